@@ -1,0 +1,153 @@
+/*
+ * ragarc_b200.h - C ABI of libragarc_b200.so: the B200 (sm_100a) retrieval hot path of RAG-ARC.
+ *
+ * Every entry point replaces a piece of arithmetic that the reference obtains from a Python
+ * third-party package on the CPU; the citation after each prototype names the reference call
+ * site (relative to /root/reference) a maintainer would re-point at this library (see
+ * INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
+ *     buffers, the library keeps no state between calls (no handles, no globals except the
+ *     thread-local error string);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *     asynchronous on that stream, re-entrant, and may be made from any host thread
+ *     (core/retrieval/base.py:82-96 runs retrievers from a thread pool);
+ *   - return value 0 = ok; anything else is a RAGARC_ERR_* code and ragarc_last_error() holds a
+ *     message for the calling thread.  Nothing throws across the ABI;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     RAGARC_ERR_CUDA.
+ */
+#ifndef RAGARC_B200_H
+#define RAGARC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAGARC_ABI_VERSION 1
+
+enum {
+  RAGARC_OK = 0,
+  RAGARC_ERR_INVALID = 1,   /* bad argument */
+  RAGARC_ERR_CUDA = 2,      /* CUDA runtime / driver error */
+  RAGARC_ERR_WORKSPACE = 3, /* workspace too small */
+  RAGARC_ERR_UNSUPPORTED = 4
+};
+
+/* storage dtype of corpus / query / encoder matrices */
+enum { RAGARC_F32 = 0, RAGARC_BF16 = 1, RAGARC_F16 = 2 };
+
+/* pooling modes (sentence-transformers Pooling module) */
+enum { RAGARC_POOL_MEAN = 0, RAGARC_POOL_CLS = 1, RAGARC_POOL_LAST = 2 };
+
+/* which dense scoring kernel ran / should run */
+enum { RAGARC_DENSE_AUTO = 0, RAGARC_DENSE_SIMT = 1, RAGARC_DENSE_TCGEN05 = 2 };
+
+int ragarc_abi_version(void);
+const char* ragarc_last_error(void);
+
+/* Number of GPU kernels this library has launched from the calling process so far (all
+ * threads).  bench.py reports the delta over its timed region as "gpu_launches". */
+uint64_t ragarc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * L2 normalise + cast.   Replaces faiss.normalize_L2 at
+ *   encapsulation/database/vector_db/VectorStore_Faiss.py:150-154 (called :178 on add, :259 on
+ *   query) and the .astype(np.float32) staging at :170,:258.
+ * src: fp32 [n,d] row-major.  dst: [n,d] of dst_dtype (may alias src when dst_dtype==F32).
+ * normalize!=0: per row nr=sum(x^2) in fp32; if nr>0 row *= 1/sqrt(nr) (zero rows untouched).
+ */
+int ragarc_normalize_cast(const float* src, void* dst, int64_t n, int d, int dst_dtype,
+                          int normalize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact dense top-k.   Replaces faiss.IndexFlatIP.search at VectorStore_Faiss.py:263
+ *   (D float32[nq,k] descending inner product, I int64[nq,k], -1 padding when k > n).
+ * corpus: [n,d] row-major, queries: [nq,d] row-major, both of `dtype`; fp32 accumulation.
+ * Equal scores are ordered by ascending row id (FAISS leaves tie order unspecified).
+ * The nq x n score matrix is never written to memory: scoring and per-query selection are
+ * fused (tcgen05 tensor-core tiles for bf16/fp16 with d % 8 == 0, fp32 SIMT tiles otherwise).
+ * `path` = RAGARC_DENSE_AUTO lets the library choose; *path_used (host, may be NULL) reports it.
+ */
+size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k);
+int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                      int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
+                      size_t workspace_bytes, int path, int* path_used_host, void* stream);
+
+/* Same search, but returns packed sortable keys for the multi-GPU merge:
+ *   key = (orderable_fp32(score) << 32) | (0xFFFFFFFF - (id_base + row)),  0 = empty slot,
+ * sorted descending per query.  One shard per GPU; id_base = first global row of the shard. */
+int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                           int nq, int k, uint64_t id_base, uint64_t* out_keys, void* workspace,
+                           size_t workspace_bytes, int path, int* path_used_host, void* stream);
+
+/* k*G-way merge after the NCCL all-gather of ragarc_dense_topk_keys outputs.
+ * keys: [nlists, nq, k_in] (as all-gathered, rank-major).  Output as ragarc_dense_topk. */
+int ragarc_merge_topk_keys(const uint64_t* keys, int nlists, int nq, int k_in, int k_out,
+                           float* out_scores, int64_t* out_ids, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BM25 (Okapi) scoring over CSR postings.   Replaces rank_bm25.BM25Okapi.get_scores at
+ *   core/retrieval/bm25.py:306,332 and np.argsort(scores)[::-1][:k] at :309,:359.
+ * indptr[V+1] (int64), post_doc/post_tf[nnz] (int32; doc ids unique inside one posting list),
+ * idf[V], doc_norm[n_docs] = k1*(1-b+b*dl/avgdl) (fp64, computed by the host exactly as the
+ * reference expression does), k1_plus_1 = k1+1.
+ * q_terms: [nq,tmax] term ids in query order, duplicates repeated, -1 = token not in the
+ * vocabulary (contributes 0) ; q_len[nq].
+ * score[d] += idf[t] * ( tf*(k1+1) / (tf + doc_norm[d]) ), fp64, each operation individually
+ * rounded (no FMA), terms accumulated in query order => bit-identical to the numpy expression.
+ * Top-k order: descending score, ties by ascending doc id (numpy's order is unspecified).
+ */
+size_t ragarc_bm25_workspace_bytes(int64_t n_docs, int nq);
+int ragarc_bm25_scores(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
+                       const double* idf, const double* doc_norm, double k1_plus_1,
+                       const int32_t* q_terms, const int32_t* q_len, int nq, int tmax,
+                       int64_t n_docs, double* out_scores /* [nq,n_docs] */, void* stream);
+int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
+                     const double* idf, const double* doc_norm, double k1_plus_1,
+                     const int32_t* q_terms, const int32_t* q_len, int nq, int tmax,
+                     int64_t n_docs, int k, double* out_scores /* [nq,k] */,
+                     int64_t* out_ids /* [nq,k] */, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Reciprocal-rank fusion.   Replaces RRFusion.fuse at core/utils/Fusion.py:45-76 for a batch.
+ * ids: [L, nq, kl] int32 document keys, rank = position+1, negative = padding (skipped).
+ * score[key] = sum over lists (in list order) of 1.0/(rrf_k + rank) in fp64; output sorted by
+ * descending score, ties by first appearance (list order, then position) - the order Python's
+ * stable sorted(reverse=True) produces.  out_ids/out_scores: [nq, top_k], padded with -1 / 0;
+ * out_count[nq] = number of valid entries.
+ */
+int ragarc_rrf_fuse(const int32_t* ids, int n_lists, int nq, int kl, double rrf_k, int top_k,
+                    int32_t* out_ids, double* out_scores, int32_t* out_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pool + L2-normalise encoder outputs.   Replaces the Pooling/Normalize tail of
+ *   SentenceTransformer.encode behind core/file_management/embeddings/huggingface.py:122-126.
+ * x: [B,T,H] of `dtype`; mask: [B,T] int32 (0/1); out: fp32 [B,H].
+ * mean: sum_t m*x / max(sum_t m, 1e-9); cls: x[:,0]; last: last unmasked token.
+ * normalize!=0: out / max(||out||_2, 1e-12).
+ */
+int ragarc_pool_normalize(const void* x, int dtype, const int32_t* mask, int B, int T, int H,
+                          int mode, int normalize, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Greedy maximal-marginal-relevance selection.   Replaces _mmr_select at
+ *   VectorStore_Faiss.py:16-62 without re-embedding the candidates (:301-304): candidate rows
+ *   are gathered from the resident corpus.
+ * cand_rows: [nq, fetch_k] int64 corpus rows (from ragarc_dense_topk; -1 = padding).
+ * out_sel: [nq, k] int32 indices INTO the candidate list (the reference returns
+ * docs_and_scores[idx]), -1 padded.
+ */
+int ragarc_mmr_select(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                      int nq, const int64_t* cand_rows, int fetch_k, int k, double lambda_mult,
+                      int32_t* out_sel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGARC_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of ``libragarc_b200.so`` (the C ABI declared in ``include/ragarc_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing, importing this module fails
+with instructions to build it, and every compute call raises if CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from ctypes import c_double, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libragarc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu"]
+
+F32, BF16, F16 = 0, 1, 2
+POOL_MEAN, POOL_CLS, POOL_LAST = 0, 1, 2
+DENSE_AUTO, DENSE_SIMT, DENSE_TCGEN05 = 0, 1, 2
+
+# every symbol include/ragarc_b200.h declares (tests/test_abi.py checks the two stay in sync)
+EXPORTS = [
+    "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_normalize_cast",
+    "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk", "ragarc_dense_topk_keys",
+    "ragarc_merge_topk_keys", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
+    "ragarc_bm25_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
+]
+
+
+def nvcc_command(out: str = LIB_PATH):
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,550",
+            *[os.path.join(CSRC, s) for s in SOURCES], "-o", out]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into the in-tree shared library."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+                                                       os.path.join(_HERE, "..", "include", "ragarc_b200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    return LIB_PATH
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. rag_arc_b200 has no CPU/PyTorch fallback: build the CUDA "
+            "library first with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or rag_arc_b200._native.build_library()).")
+    lib = ctypes.CDLL(LIB_PATH)
+    P = c_void_p
+    sig = {
+        "ragarc_abi_version": (c_int, []),
+        "ragarc_last_error": (ctypes.c_char_p, []),
+        "ragarc_launch_count": (c_uint64, []),
+        "ragarc_normalize_cast": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
+        "ragarc_dense_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
+        "ragarc_dense_topk": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, P, P, P, c_size_t,
+                                      c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_dense_topk_keys": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P,
+                                           c_size_t, c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_merge_topk_keys": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
+        "ragarc_bm25_workspace_bytes": (c_size_t, [c_int64, c_int]),
+        "ragarc_bm25_scores": (c_int, [P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, P, P]),
+        "ragarc_bm25_topk": (c_int, [P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
+                                     P, c_size_t, P]),
+        "ragarc_rrf_fuse": (c_int, [P, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),
+        "ragarc_pool_normalize": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+        "ragarc_mmr_select": (c_int, [P, c_int64, c_int, c_int, P, c_int, P, c_int, c_int, c_double, P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ragarc_abi_version() != 1:
+        raise ImportError("libragarc_b200.so ABI version mismatch; rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+class RagArcError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.ragarc_last_error().decode("utf-8", "replace")
+        raise RagArcError(f"{what or 'ragarc'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib.ragarc_launch_count())

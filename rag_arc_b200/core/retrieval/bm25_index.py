@@ -1,0 +1,127 @@
+"""Host-side BM25 index build: tokenised corpus -> CSR postings + fp64 tables on the GPU.
+
+Builds exactly the statistics ``rank_bm25.BM25Okapi.__init__`` derives (the constructor the
+reference calls at /root/reference core/retrieval/bm25.py:218): per-document term frequencies and
+lengths, ``avgdl``, document frequencies, ``idf = log(N-n+0.5) - log(n+0.5)`` with the
+``epsilon * mean(idf)`` floor for negative values, defaults ``k1=1.5, b=0.75, epsilon=0.25``.
+The idf table is computed with Python ``math.log`` and summed in first-seen vocabulary order so
+that every fp64 value is bit-identical to what the reference holds; the per-document length
+normaliser ``k1*(1-b+b*dl/avgdl)`` is evaluated with numpy in the reference's operation order.
+Index build is host work (not the optimisation target); scoring is ``ragarc_bm25_topk``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+class Bm25Index:
+    def __init__(self, *, vocab: Optional[Dict[str, int]], indptr: np.ndarray, post_doc: np.ndarray,
+                 post_tf: np.ndarray, doc_len: np.ndarray, k1: float, b: float, epsilon: float,
+                 device):
+        self.vocab = vocab
+        self.k1, self.b, self.epsilon = k1, b, epsilon
+        self.n_docs = int(doc_len.shape[0])
+        self.doc_len_np = doc_len.astype(np.int64)
+        self.avgdl = int(self.doc_len_np.sum()) / self.n_docs
+        df = np.diff(indptr)
+        V = int(df.shape[0])
+        N = self.n_docs
+        idf = np.empty(V, np.float64)
+        total = 0.0
+        log = math.log
+        for ti in range(V):          # first-seen order, sequential Python-float sum
+            n_t = int(df[ti])
+            val = log(N - n_t + 0.5) - log(n_t + 0.5)
+            idf[ti] = val
+            total += val
+        self.average_idf = total / V if V else 0.0
+        idf[idf < 0] = epsilon * self.average_idf
+        self.idf_np = idf
+        self.doc_norm_np = k1 * (1 - b + b * self.doc_len_np / self.avgdl)
+        self.k1_plus_1 = k1 + 1
+        self.indptr_np, self.post_doc_np, self.post_tf_np = indptr, post_doc, post_tf
+        self.device = torch.device(device)
+        self.indptr = torch.from_numpy(indptr.astype(np.int64)).to(self.device)
+        self.post_doc = torch.from_numpy(post_doc.astype(np.int32)).to(self.device)
+        self.post_tf = torch.from_numpy(post_tf.astype(np.int32)).to(self.device)
+        self.idf = torch.from_numpy(idf).to(self.device)
+        self.doc_norm = torch.from_numpy(self.doc_norm_np).to(self.device)
+
+    # -- construction --------------------------------------------------------------------------
+    @classmethod
+    def from_token_lists(cls, corpus: Sequence[Sequence[str]], *, k1: float = 1.5, b: float = 0.75,
+                         epsilon: float = 0.25, device="cuda") -> "Bm25Index":
+        vocab: Dict[str, int] = {}
+        flat: List[int] = []
+        lens = np.empty(len(corpus), np.int64)
+        get = vocab.get
+        for di, tokens in enumerate(corpus):
+            lens[di] = len(tokens)
+            for tok in tokens:
+                ti = get(tok)
+                if ti is None:
+                    ti = len(vocab)
+                    vocab[tok] = ti
+                flat.append(ti)
+        toks = np.asarray(flat, dtype=np.int64)
+        offs = np.zeros(len(corpus) + 1, np.int64)
+        np.cumsum(lens, out=offs[1:])
+        return cls._from_ids(toks, offs, len(vocab), vocab, k1, b, epsilon, device)
+
+    @classmethod
+    def from_token_ids(cls, toks: np.ndarray, offs: np.ndarray, *, k1: float = 1.5, b: float = 0.75,
+                       epsilon: float = 0.25, device="cuda") -> "Bm25Index":
+        """Corpus given as integer token ids (synthetic corpora).  Term ids are re-numbered in
+        first-seen order, which is the order the reference's idf mean is accumulated in; the
+        vocabulary maps the *original* id (as ``t<id>`` string and as int) to the new one."""
+        toks = np.asarray(toks, dtype=np.int64)
+        uniq, first = np.unique(toks, return_index=True)
+        order = np.argsort(first, kind="stable")
+        remap = np.empty(int(uniq.max()) + 1, np.int64)
+        remap[:] = -1
+        remap[uniq[order]] = np.arange(len(uniq))
+        idx = cls._from_ids(remap[toks], np.asarray(offs, np.int64), len(uniq), None, k1, b, epsilon, device)
+        idx.id_remap = remap
+        return idx
+
+    @classmethod
+    def _from_ids(cls, toks, offs, V, vocab, k1, b, epsilon, device):
+        n_docs = len(offs) - 1
+        lens = np.diff(offs)
+        doc_of = np.repeat(np.arange(n_docs, dtype=np.int64), lens)
+        pair = toks * n_docs + doc_of                 # sorts by term, then doc
+        upair, tf = np.unique(pair, return_counts=True)
+        term = upair // n_docs
+        post_doc = (upair % n_docs).astype(np.int32)
+        indptr = np.zeros(V + 1, np.int64)
+        np.cumsum(np.bincount(term, minlength=V), out=indptr[1:])
+        return cls(vocab=vocab, indptr=indptr, post_doc=post_doc, post_tf=tf.astype(np.int32),
+                   doc_len=lens, k1=k1, b=b, epsilon=epsilon, device=device)
+
+    # -- queries -------------------------------------------------------------------------------
+    def encode_queries(self, queries: Iterable[Sequence[str]]):
+        """Token lists -> (q_terms int32 [nq,tmax] with -1 for out-of-vocabulary tokens, q_len)."""
+        rows = [[self.vocab.get(tok, -1) for tok in q] for q in queries]
+        return self._pack(rows)
+
+    def encode_query_ids(self, qids: np.ndarray):
+        """Integer-token queries for an index built with ``from_token_ids``."""
+        qids = np.asarray(qids, np.int64)
+        safe = np.where((qids >= 0) & (qids < len(self.id_remap)), qids, 0)
+        mapped = np.where((qids >= 0) & (qids < len(self.id_remap)), self.id_remap[safe], -1)
+        q_terms = torch.from_numpy(mapped.astype(np.int32)).to(self.device)
+        q_len = torch.full((qids.shape[0],), qids.shape[1], dtype=torch.int32, device=self.device)
+        return q_terms.contiguous(), q_len
+
+    def _pack(self, rows):
+        tmax = max(1, max((len(r) for r in rows), default=1))
+        arr = np.full((len(rows), tmax), -1, np.int32)
+        ln = np.zeros(len(rows), np.int32)
+        for i, r in enumerate(rows):
+            arr[i, :len(r)] = r
+            ln[i] = len(r)
+        return (torch.from_numpy(arr).to(self.device), torch.from_numpy(ln).to(self.device))

@@ -1,0 +1,148 @@
+// Error plumbing, launch accounting, the dense-search planner and the dense C-ABI entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace ragarc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+static int cap_for_k(int k) {
+  if (k <= 224) return 512;
+  if (k <= 480) return 1024;
+  if (k <= 992) return 2048;
+  if (k <= 2016) return 4096;
+  return 0;
+}
+
+int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* pl, int* path_out) {
+  RA_REQUIRE(n >= 0 && d > 0 && nq >= 0 && k > 0, "dense: bad shape n=%lld d=%d nq=%d k=%d",
+             (long long)n, d, nq, k);
+  RA_REQUIRE(dtype == RAGARC_F32 || dtype == RAGARC_BF16 || dtype == RAGARC_F16, "dense: bad dtype %d", dtype);
+  RA_REQUIRE(n < (int64_t)0xFFFFFFF0ll, "dense: at most 2^32-16 rows per shard");
+  int cap = cap_for_k(k);
+  if (!cap) { set_error("dense: k=%d > 2016 unsupported", k); return RAGARC_ERR_UNSUPPORTED; }
+  int use = path;
+  if (use == RAGARC_DENSE_AUTO)
+    use = (dtype != RAGARC_F32 && d % 8 == 0) ? RAGARC_DENSE_TCGEN05 : RAGARC_DENSE_SIMT;
+  if (use == RAGARC_DENSE_TCGEN05 && (dtype == RAGARC_F32 || d % 8 != 0)) {
+    set_error("dense: tcgen05 path needs bf16/fp16 and d %% 8 == 0");
+    return RAGARC_ERR_UNSUPPORTED;
+  }
+  *path_out = use;
+  const bool tc = use == RAGARC_DENSE_TCGEN05;
+  pl->rows_per_item = tc ? 128 : 64;
+  pl->tile_n = tc ? 256 : 64;
+  pl->MB = (int)ceil_div(nq > 0 ? nq : 1, pl->rows_per_item);
+  pl->tiles = ceil_div(n > 0 ? n : 1, pl->tile_n);
+  pl->cap = cap;
+  int64_t target_items = (int64_t)sm_count() * (tc ? 2 : 4);
+  int64_t S = (target_items + pl->MB / 2) / pl->MB;
+  if (S < 1) S = 1;
+  if (S > pl->tiles) S = pl->tiles;
+  int64_t smax = 8192 / k;            // merge kernel sorts S*k keys in shared memory
+  if (smax < 1) smax = 1;
+  if (S > smax) S = smax;
+  pl->S = (int)S;
+  size_t items = (size_t)pl->MB * pl->S;
+  size_t off = 0;
+  pl->off_lists = off;  off = align_up(off + items * pl->rows_per_item * (size_t)cap * 8, 256);
+  pl->off_counts = off; off = align_up(off + items * pl->rows_per_item * 4, 256);
+  pl->off_gthr = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * 4, 256);
+  pl->off_keys = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * k * 8, 256);
+  pl->total = off;
+  return RAGARC_OK;
+}
+
+static int dense_common(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                        int k, uint64_t id_base, uint64_t* out_keys, float* out_scores,
+                        int64_t* out_ids, void* workspace, size_t workspace_bytes, int path,
+                        int* path_used_host, cudaStream_t stream) {
+  DensePlan pl;
+  int use = 0;
+  if (path == RAGARC_DENSE_AUTO && !dense_tc_supported(corpus, n, d, dtype, queries)) path = RAGARC_DENSE_SIMT;
+  int rc = plan_dense(n, d, dtype, nq, k, path, &pl, &use);
+  if (rc) return rc;
+  if (path_used_host) *path_used_host = use;
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(corpus || n == 0, "dense: null corpus");
+  RA_REQUIRE(queries, "dense: null queries");
+  RA_REQUIRE(workspace && workspace_bytes >= pl.total, "dense: workspace %zu < required %zu",
+             workspace_bytes, pl.total);
+  RA_REQUIRE(((uintptr_t)workspace & 255) == 0, "dense: workspace must be 256-byte aligned");
+  char* ws = (char*)workspace;
+  uint64_t* lists = (uint64_t*)(ws + pl.off_lists);
+  int* counts = (int*)(ws + pl.off_counts);
+  uint32_t* gthr = (uint32_t*)(ws + pl.off_gthr);
+  RA_CUDA(cudaMemsetAsync(counts, 0, (pl.off_keys - pl.off_counts), stream));  // counts + gthr
+  if (n > 0) {
+    if (use == RAGARC_DENSE_TCGEN05)
+      rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, stream);
+    else
+      rc = launch_dense_simt(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, stream);
+    if (rc) return rc;
+  }
+  return launch_merge_lists(lists, counts, pl, nq, k, id_base, out_keys, out_scores, out_ids, stream);
+}
+
+}  // namespace ragarc
+
+using namespace ragarc;
+
+extern "C" {
+
+int ragarc_abi_version(void) { return RAGARC_ABI_VERSION; }
+const char* ragarc_last_error(void) { return g_err; }
+uint64_t ragarc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k) {
+  // worst case over the two paths so that the caller can size once
+  size_t best = 0;
+  for (int path : {RAGARC_DENSE_SIMT, RAGARC_DENSE_TCGEN05}) {
+    DensePlan pl;
+    int use;
+    if (path == RAGARC_DENSE_TCGEN05 && (dtype == RAGARC_F32 || d % 8 != 0)) continue;
+    if (plan_dense(n, d, dtype, nq, k, path, &pl, &use) == RAGARC_OK && pl.total > best) best = pl.total;
+  }
+  return best;
+}
+
+int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                      int k, float* out_scores, int64_t* out_ids, void* workspace,
+                      size_t workspace_bytes, int path, int* path_used_host, void* stream) {
+  RA_REQUIRE(out_scores && out_ids, "dense_topk: null outputs");
+  return dense_common(corpus, n, d, dtype, queries, nq, k, 0, nullptr, out_scores, out_ids, workspace,
+                      workspace_bytes, path, path_used_host, (cudaStream_t)stream);
+}
+
+int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                           int nq, int k, uint64_t id_base, uint64_t* out_keys, void* workspace,
+                           size_t workspace_bytes, int path, int* path_used_host, void* stream) {
+  RA_REQUIRE(out_keys, "dense_topk_keys: null output");
+  RA_REQUIRE(id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_keys: global ids must fit 32 bits");
+  return dense_common(corpus, n, d, dtype, queries, nq, k, id_base, out_keys, nullptr, nullptr,
+                      workspace, workspace_bytes, path, path_used_host, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+// Shared device/host helpers for libragarc_b200: error plumbing, sortable keys, and the
+// per-query candidate-list machinery (append / warp-cooperative prune) that both dense scoring
+// kernels use so that the nq x n score matrix never reaches HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ragarc_b200.h"
+
+namespace ragarc {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define RA_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::ragarc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                          cudaGetErrorString(_e));                                        \
+      return RAGARC_ERR_CUDA;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define RA_REQUIRE(cond, ...)                                                             \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::ragarc::set_error(__VA_ARGS__);                                                   \
+      return RAGARC_ERR_INVALID;                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define RA_LAUNCH_CHECK()                                                                 \
+  do {                                                                                    \
+    ::ragarc::count_launch();                                                             \
+    RA_CUDA(cudaGetLastError());                                                          \
+  } while (0)
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- sortable keys -------------------------------------------------------------------------
+// fp32 -> uint32 that sorts like the float (NaN excluded); -0 is canonicalised to +0.
+// ord 0 is never produced by a real score and doubles as "unset".
+__host__ __device__ __forceinline__ uint32_t f32_to_ord(float f) {
+  f += 0.0f;
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_to_f32(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+constexpr uint32_t ORD_NEG_INF = 0x007FFFFFu;
+
+// key: larger = better (higher score, then LOWER row id).  0 = empty slot.
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return (uint64_t(f32_to_ord(score)) << 32) | uint64_t(0xFFFFFFFFu - row);
+}
+__device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xFFFFFFFFu - uint32_t(key); }
+__device__ __forceinline__ float key_score(uint64_t key) { return ord_to_f32(uint32_t(key >> 32)); }
+
+// Strict float threshold equivalent to "ord(v) > T" (T==0 / below -inf: everything finite passes).
+__device__ __forceinline__ float thr_from_ord(uint32_t T) {
+  return (T <= ORD_NEG_INF) ? -INFINITY : ord_to_f32(T);
+}
+// Threshold for a query given its CTA-local k-th best (strict: later rows with an equal score
+// have higher ids and lose the tie) and the cross-CTA shared k-th best (non-strict: the rows
+// behind it may have higher ids than ours).
+__device__ __forceinline__ float combine_thr(uint32_t ord_local, uint32_t ord_global) {
+  uint32_t g = ord_global ? ord_global - 1 : 0;
+  return thr_from_ord(ord_local > g ? ord_local : g);
+}
+
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// ---- warp-cooperative prune -------------------------------------------------------------------
+// Keeps exactly the k largest keys of list[0..n) (n > k, keys distinct) at list[0..k) and
+// returns ord of the k-th largest score.  MSB-first 8-bit radix select over the 64-bit keys with
+// early exit as soon as the boundary bucket is entirely inside the top-k (typically 2-3 passes
+// for float scores), then an in-place stable compaction.  All 32 lanes must call it with the
+// same arguments; `hist` is 256 words of shared memory private to the warp.
+static __device__ __noinline__ uint32_t warp_prune(uint64_t* __restrict__ list, int n, int k,
+                                            uint32_t* hist) {
+  const int lane = threadIdx.x & 31;
+  uint64_t prefix = 0, mask = 0;
+  uint32_t rem = (uint32_t)k;
+  __syncwarp();
+#pragma unroll 1
+  for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      uint64_t key = list[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xFFu], 1u);
+    }
+    __syncwarp();
+    uint32_t h[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+    uint32_t incl = sum;                       // becomes: sum over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_down_sync(FULL, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    uint32_t excl = incl - sum;                // keys in buckets above this lane's 8 buckets
+    bool here = (excl < rem) && (incl >= rem);
+    int src = __ffs(__ballot_sync(FULL, here)) - 1;
+    uint32_t D = 0, above = 0, hD = 0;
+    if (lane == src) {
+      uint32_t acc = excl;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (acc + h[j] >= rem) { D = 8 * lane + j; above = acc; hD = h[j]; break; }
+        acc += h[j];
+      }
+    }
+    D = __shfl_sync(FULL, D, src);
+    above = __shfl_sync(FULL, above, src);
+    hD = __shfl_sync(FULL, hD, src);
+    rem -= above;
+    prefix |= uint64_t(D) << shift;
+    mask |= uint64_t(0xFF) << shift;
+    if (hD == rem) break;                      // whole boundary bucket is kept
+  }
+  // keep <=> (key & mask) >= prefix : exactly k keys
+  int base = 0;
+  uint32_t min_ord = 0xFFFFFFFFu;
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    int i = r0 + lane;
+    uint64_t key = (i < n) ? list[i] : 0ull;
+    bool keep = (i < n) && ((key & mask) >= prefix);
+    unsigned b = __ballot_sync(FULL, keep);
+    if (keep) {
+      list[base + __popc(b & ((1u << lane) - 1u))] = key;
+      min_ord = min(min_ord, uint32_t(key >> 32));
+    }
+    base += __popc(b);
+  }
+  __syncwarp();
+  return warp_min_u32(min_ord);
+}
+
+// Per-thread (= per query row) running state of the fused selection.
+struct RowState {
+  uint64_t* list;     // this (item,row)'s candidate list, capacity `cap` keys
+  int cnt;
+  uint32_t ord_local; // ord of the k-th best kept so far in THIS list (0 = list never pruned)
+  uint32_t ord_global;// last value read from the cross-CTA shared threshold
+  float thr;          // strict pass threshold
+};
+
+// Called warp-uniformly after a chunk of at most `chunk` appends per lane: prunes every lane's
+// list that could overflow on the next chunk.  gthr_row = &shared_threshold[query] or nullptr.
+__device__ __forceinline__ void prune_if_needed(RowState& st, int k, int cap, int chunk,
+                                                uint32_t* gthr_row, uint32_t* hist, bool force) {
+  const int lane = threadIdx.x & 31;
+  bool need = force ? (st.cnt > k) : (st.cnt > cap - chunk);
+  unsigned m = __ballot_sync(FULL, need);
+  while (m) {
+    int src = __ffs(m) - 1;
+    m &= m - 1;
+    unsigned long long lp = (unsigned long long)st.list;
+    lp = __shfl_sync(FULL, lp, src);
+    int n = __shfl_sync(FULL, st.cnt, src);
+    uint32_t kth = warp_prune((uint64_t*)lp, n, k, hist);
+    if (lane == src) {
+      st.cnt = k;
+      st.ord_local = kth;
+      if (gthr_row) {
+        uint32_t old = atomicMax(gthr_row, kth);
+        st.ord_global = old > kth ? old : kth;
+      }
+      st.thr = combine_thr(st.ord_local, st.ord_global);
+    }
+  }
+}
+
+// Workspace plan shared by both dense paths (host side).
+struct DensePlan {
+  int rows_per_item;   // query rows per work item (128 tcgen05, 64 simt)
+  int tile_n;          // corpus rows per tile
+  int MB;              // query blocks
+  int S;               // corpus slices
+  int64_t tiles;       // total corpus tiles
+  int cap;             // list capacity (keys)
+  size_t off_lists, off_counts, off_gthr, off_keys, total;
+};
+
+int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* plan, int* path_out);
+
+int launch_dense_simt(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                      int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
+                      cudaStream_t stream);
+int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
+                    cudaStream_t stream);
+bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries);
+
+// merge of per-slice candidate lists -> sorted keys [nq,k] (+ optional decoded outputs)
+int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
+                       uint64_t id_base, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                       cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace ragarc

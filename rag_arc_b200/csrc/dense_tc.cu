@@ -1,0 +1,317 @@
+// Dense scoring on the 5th-generation tensor cores with the per-query selection fused into the
+// epilogue (sm_100a only).
+//
+//   scores[q, r] = sum_k Q[q,k] * X[r,k]          bf16/fp16 operands, fp32 accumulate in TMEM
+//
+// Work item = (query block of 128 rows, contiguous slice of corpus tiles); a persistent CTA walks
+// its items.  Per corpus tile (256 rows) and per 64-wide k block, one elected thread issues TMA
+// loads of the Q tile [128x64] and the X tile [256x64] into 128B-swizzled shared memory (4-stage
+// mbarrier ring); one elected thread issues tcgen05.mma (M=128, N=256, K=16, cta_group::1) into
+// one of two 256-column TMEM accumulators; four epilogue warps read the finished accumulator
+// with tcgen05.ld (32 lanes x 32 columns: one thread == one query row), compare every score with
+// the query's running threshold in registers and append the survivors to the (item,row)
+// candidate list; lists are pruned warp-cooperatively (common.cuh).  The nq x n score matrix
+// never leaves the SM.  While the epilogue drains accumulator b, the MMA warp fills b^1.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ragarc {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps (error returned to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile in 128B-swizzled shared memory (rows of 64 bf16 = 128 B, 8-row groups
+// 1024 B apart): start>>4 | LBO(ignored for swizzled K-major)=1 | SBO=1024>>4 | version=1 | SW128.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Params {
+  int64_t n;       // corpus rows
+  int nq, k, num_kb, MB, S;
+  int64_t tiles;
+  int cap;
+  uint32_t idesc;
+  uint64_t* lists;
+  int* counts;
+  uint32_t* gthr;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles_smem = smem;                                    // STAGES x (A | B)
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);  // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                       // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;                      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint32_t* hist = (uint32_t*)(smem + STAGES * STAGE_BYTES + 256);  // [4][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t items = (int64_t)p.MB * p.S;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int qb = (int)(item % p.MB);
+        const int64_t s = item / p.MB;
+        const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+        for (int64_t t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a = tiles_smem + stage * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(a, &tmap_q, &full_bar[stage], kb * BK, qb * BM);
+            tma_load_2d(a + A_BYTES, &tmap_x, &full_bar[stage], kb * BK, (int)(t * BN));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t tcount = 0;
+      for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t s = item / p.MB;
+        const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+        for (int64_t t = t0; t < t1; ++t, ++tcount) {
+          const uint32_t buf = tcount & 1, aphase = (tcount >> 1) & 1;
+          mbar_wait(&tempty_bar[buf], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a = smem_u32(tiles_smem + stage * STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(a);
+            const uint64_t bdesc = make_smem_desc(a + A_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address
+              tc_mma(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
+                     (uint32_t)((kb | k4) != 0));
+            }
+            tc_commit(&empty_bar[stage]);      // frees the smem stage when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&tfull_bar[buf]);          // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ----------------------
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // query row inside the block == TMEM lane
+    uint32_t* myhist = hist + (warp - 2) * 256;
+    uint32_t tcount = 0;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+      const int qb = (int)(item % p.MB);
+      const int64_t s = item / p.MB;
+      const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+      const int qrow = qb * BM + row;
+      RowState st;
+      st.list = p.lists + ((size_t)item * BM + row) * (size_t)p.cap;
+      st.cnt = 0;
+      st.ord_local = 0;
+      st.ord_global = 0;
+      st.thr = (qrow < p.nq) ? -INFINITY : INFINITY;
+      uint32_t* grow = (qrow < p.nq) ? p.gthr + qrow : nullptr;
+      for (int64_t t = t0; t < t1; ++t, ++tcount) {
+        const uint32_t buf = tcount & 1, aphase = (tcount >> 1) & 1;
+        if (grow) {
+          uint32_t g = *(volatile uint32_t*)grow;
+          if (g > st.ord_global) { st.ord_global = g; st.thr = combine_thr(st.ord_local, g); }
+        }
+        const int64_t r0 = t * BN;
+        const int nvalid = (int)((p.n - r0) < BN ? (p.n - r0) : BN);
+        mbar_wait(&tfull_bar[buf], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (c0 >= nvalid) break;                // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float f = __uint_as_float(v[j]);
+            if (f > st.thr) {
+              if (c0 + j < nvalid) st.list[st.cnt++] = make_key(f, (uint32_t)(r0 + c0 + j));
+            }
+          }
+          prune_if_needed(st, p.k, p.cap, 32, grow, myhist, false);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+      prune_if_needed(st, p.k, p.cap, 32, grow, myhist, true);
+      p.counts[(size_t)item * BM + row] = st.cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int dtype, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return RAGARC_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == RAGARC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return RAGARC_ERR_CUDA; }
+  return RAGARC_OK;
+}
+
+}  // namespace tc
+
+bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries) {
+  if (dtype != RAGARC_BF16 && dtype != RAGARC_F16) return false;
+  if (d % 8 != 0 || n <= 0) return false;
+  if (((uintptr_t)corpus & 15) || ((uintptr_t)queries & 15)) return false;
+  return true;
+}
+
+int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
+                    cudaStream_t stream) {
+  using namespace tc;
+  RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
+             "dense tcgen05: needs bf16/fp16, d %% 8 == 0 and 16-byte aligned base pointers");
+  CUtensorMap mq, mx;
+  int rc = make_map(&mq, queries, nq, d, dtype, BM);
+  if (rc) return rc;
+  rc = make_map(&mx, corpus, n, d, dtype, BN);
+  if (rc) return rc;
+  Params p;
+  p.n = n; p.nq = nq; p.k = k; p.num_kb = (d + BK - 1) / BK; p.MB = pl.MB; p.S = pl.S;
+  p.tiles = pl.tiles; p.cap = pl.cap; p.lists = lists; p.counts = counts; p.gthr = gthr;
+  const uint32_t fmt = dtype == RAGARC_BF16 ? 1u : 0u;
+  // instruction descriptor (kind::f16): D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major,
+  // N>>3 at [17,23), M>>4 at [24,29)
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t items = (int64_t)pl.MB * pl.S;
+  int grid = (int)(items < sm_count() ? items : sm_count());
+  dense_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(mq, mx, p);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+}  // namespace ragarc

@@ -1,0 +1,298 @@
+// Small kernels either side of the search: L2-normalise + cast (index add / query staging),
+// pool + normalise of encoder outputs, reciprocal-rank fusion, greedy MMR selection.
+#include "common.cuh"
+
+namespace ragarc {
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T> __device__ __forceinline__ float load_f32(const T* p);
+template <> __device__ __forceinline__ float load_f32<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float load_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float load_f32<__half>(const __half* p) { return __half2float(*p); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ---- normalize + cast: one warp per row (faiss.normalize_L2 semantics) ------------------------
+template <typename T>
+__global__ void normalize_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n, int d,
+                                      int normalize) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = src + (size_t)row * d;
+  T* o = dst + (size_t)row * d;
+  float scale = 1.0f;
+  if (normalize) {
+    float nr = 0.f;
+    for (int i = lane; i < d; i += 32) { float v = s[i]; nr = fmaf(v, v, nr); }
+    nr = warp_sum(nr);
+    if (nr > 0.f) scale = __fdiv_rn(1.0f, __fsqrt_rn(nr));
+  }
+  for (int i = lane; i < d; i += 32) o[i] = from_f32<T>(__fmul_rn(s[i], scale));
+}
+
+// ---- pool + normalize: one CTA per sequence ---------------------------------------------------
+template <typename T>
+__global__ void pool_normalize_kernel(const T* __restrict__ x, const int32_t* __restrict__ mask, int T_len,
+                                      int H, int mode, int normalize, float* __restrict__ out) {
+  extern __shared__ float sred[];     // [blockDim/32]
+  __shared__ float s_cnt;
+  __shared__ int s_last;
+  const int b = blockIdx.x;
+  const T* xb = x + (size_t)b * T_len * H;
+  const int32_t* mb = mask + (size_t)b * T_len;
+  if (threadIdx.x < 32) {
+    // token count (as float, like the reference's mask.sum) and index of the last kept token
+    float c = 0.f; int last = -1;
+    for (int t = threadIdx.x; t < T_len; t += 32) if (mb[t] != 0) { c += 1.f; last = t; }
+    c = warp_sum(c);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) last = max(last, __shfl_xor_sync(FULL, last, o));
+    if (threadIdx.x == 0) { s_cnt = c; s_last = last; }
+  }
+  __syncthreads();
+  const float cnt = s_cnt;
+  float sq = 0.f;
+  // each thread owns columns h = tid, tid+blockDim, ... ; tokens are summed in order
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float v;
+    if (mode == RAGARC_POOL_MEAN) {
+      float acc = 0.f;
+      for (int t = 0; t < T_len; ++t)
+        if (mb[t] != 0) acc += load_f32<T>(xb + (size_t)t * H + h);
+      v = __fdiv_rn(acc, fmaxf(cnt, 1e-9f));
+    } else if (mode == RAGARC_POOL_CLS) {
+      v = load_f32<T>(xb + h);
+    } else {
+      // last token: left-padded batches (mask[T-1]==1) -> T-1, else index of last kept token
+      int t = s_last < 0 ? 0 : s_last;
+      v = load_f32<T>(xb + (size_t)t * H + h);
+    }
+    out[(size_t)b * H + h] = v;
+    sq = fmaf(v, v, sq);
+  }
+  if (!normalize) return;
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sred[w];
+  const float inv_den = fmaxf(__fsqrt_rn(tot), 1e-12f);
+  for (int h = threadIdx.x; h < H; h += blockDim.x)
+    out[(size_t)b * H + h] = __fdiv_rn(out[(size_t)b * H + h], inv_den);
+}
+
+// ---- reciprocal-rank fusion: one CTA per query ------------------------------------------------
+// Positions p = l*kl + i walk the lists in the reference's order (Fusion.py:55-61).  The first
+// position holding a key owns its score; contributions are added in position order (fp64, each
+// 1.0/(k+rank) correctly rounded) so the sums equal Python's.  Output order = Python's stable
+// sorted(reverse=True): descending score, ties by first appearance.
+__global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, int kl, double rrf_k,
+                                int top_k, int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                                int32_t* __restrict__ out_count) {
+  extern __shared__ unsigned char rrf_smem[];
+  const int n = L * kl;
+  int32_t* key = (int32_t*)rrf_smem;                    // [n]
+  double* score = (double*)(rrf_smem + (((size_t)n * 4 + 7) & ~(size_t)7));   // [n], valid for owners
+  __shared__ int n_owner;
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) n_owner = 0;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int l = p / kl, i = p % kl;
+    key[p] = ids[((size_t)l * nq + q) * kl + i];
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const int32_t me = key[p];
+    double s = -1.0;   // < 0 : not an owner
+    if (me >= 0) {
+      bool first = true;
+      for (int j = 0; j < p; ++j) if (key[j] == me) { first = false; break; }
+      if (first) {
+        s = 0.0;
+        for (int j = p; j < n; ++j)
+          if (key[j] == me) s = __dadd_rn(s, __ddiv_rn(1.0, __dadd_rn(rrf_k, (double)(j % kl + 1))));
+        atomicAdd(&n_owner, 1);
+      }
+    }
+    score[p] = s;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const double s = score[p];
+    if (s < 0.0) continue;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double t = score[j];
+      if (t >= 0.0 && (t > s || (t == s && j < p))) ++rank;
+    }
+    if (rank < top_k) {
+      out_ids[(size_t)q * top_k + rank] = key[p];
+      out_scores[(size_t)q * top_k + rank] = s;
+    }
+  }
+  const int cnt = n_owner < top_k ? n_owner : top_k;
+  for (int j = cnt + threadIdx.x; j < top_k; j += blockDim.x) {
+    out_ids[(size_t)q * top_k + j] = -1;
+    out_scores[(size_t)q * top_k + j] = 0.0;
+  }
+  if (threadIdx.x == 0) out_count[q] = cnt;
+}
+
+// ---- greedy MMR: one CTA per query ------------------------------------------------------------
+// Restates _mmr_select (VectorStore_Faiss.py:16-62): first pick = candidate 0; then k-1 times pick
+// argmax over the remaining of  lambda*<q,c> - (1-lambda)*max(0, max_sel <s,c>)  (first maximum wins,
+// python max()).  Dots are fp64 over the stored rows.
+template <typename T>
+__global__ void mmr_select_kernel(const T* __restrict__ X, int d, const T* __restrict__ Q,
+                                  const int64_t* __restrict__ cand, int fetch_k, int k, double lambda,
+                                  int32_t* __restrict__ out_sel) {
+  extern __shared__ double mmr_smem[];
+  double* qsim = mmr_smem;                 // [fetch_k]
+  double* maxsim = qsim + fetch_k;         // [fetch_k]
+  double* red = maxsim + fetch_k;          // [fetch_k] scratch scores
+  __shared__ int s_pick, s_nvalid;
+  int* taken = (int*)(red + fetch_k);      // [fetch_k]
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int64_t* c = cand + (size_t)q * fetch_k;
+  if (threadIdx.x == 0) {
+    int nv = 0;
+    while (nv < fetch_k && c[nv] >= 0) ++nv;
+    s_nvalid = nv;
+  }
+  __syncthreads();
+  const int nv = s_nvalid;
+  for (int i = warp; i < nv; i += nwarp) {
+    const T* row = X + (size_t)c[i] * d;
+    const T* qq = Q + (size_t)q * d;
+    double acc = 0.0;
+    for (int e = lane; e < d; e += 32) acc += (double)load_f32<T>(row + e) * (double)load_f32<T>(qq + e);
+    acc = warp_sum_f64(acc);
+    if (lane == 0) { qsim[i] = acc; maxsim[i] = 0.0; taken[i] = 0; }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) out_sel[(size_t)q * k + j] = -1;
+  __syncthreads();
+  if (nv == 0) return;
+  if (k >= nv) {   // reference returns all candidates in order
+    for (int j = threadIdx.x; j < nv && j < k; j += blockDim.x) out_sel[(size_t)q * k + j] = j;
+    return;
+  }
+  int pick = 0;
+  for (int step = 0; step < k; ++step) {
+    if (threadIdx.x == 0) { out_sel[(size_t)q * k + step] = pick; taken[pick] = 1; }
+    __syncthreads();
+    if (step == k - 1) break;
+    const T* prow = X + (size_t)c[pick] * d;
+    for (int i = warp; i < nv; i += nwarp) {
+      if (taken[i]) continue;
+      const T* row = X + (size_t)c[i] * d;
+      double acc = 0.0;
+      for (int e = lane; e < d; e += 32) acc += (double)load_f32<T>(row + e) * (double)load_f32<T>(prow + e);
+      acc = warp_sum_f64(acc);
+      if (lane == 0) {
+        if (acc > maxsim[i]) maxsim[i] = acc;
+        red[i] = lambda * qsim[i] - (1.0 - lambda) * maxsim[i];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = -1; double bs = 0.0;
+      for (int i = 0; i < nv; ++i) {
+        if (taken[i]) continue;
+        if (best < 0 || red[i] > bs) { best = i; bs = red[i]; }
+      }
+      s_pick = best;
+    }
+    __syncthreads();
+    pick = s_pick;
+  }
+}
+
+}  // namespace ragarc
+
+using namespace ragarc;
+
+extern "C" {
+
+int ragarc_normalize_cast(const float* src, void* dst, int64_t n, int d, int dst_dtype, int normalize,
+                          void* stream) {
+  RA_REQUIRE(n >= 0 && d > 0, "normalize_cast: bad shape n=%lld d=%d", (long long)n, d);
+  if (n == 0) return RAGARC_OK;
+  RA_REQUIRE(src && dst, "normalize_cast: null pointer");
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(n, warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == RAGARC_F32) normalize_cast_kernel<float><<<grid, warps * 32, 0, st>>>(src, (float*)dst, n, d, normalize);
+  else if (dst_dtype == RAGARC_BF16) normalize_cast_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>(src, (__nv_bfloat16*)dst, n, d, normalize);
+  else if (dst_dtype == RAGARC_F16) normalize_cast_kernel<__half><<<grid, warps * 32, 0, st>>>(src, (__half*)dst, n, d, normalize);
+  else { set_error("normalize_cast: bad dtype %d", dst_dtype); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_pool_normalize(const void* x, int dtype, const int32_t* mask, int B, int T, int H, int mode,
+                          int normalize, float* out, void* stream) {
+  RA_REQUIRE(B >= 0 && T > 0 && H > 0, "pool_normalize: bad shape B=%d T=%d H=%d", B, T, H);
+  RA_REQUIRE(mode >= RAGARC_POOL_MEAN && mode <= RAGARC_POOL_LAST, "pool_normalize: bad mode %d", mode);
+  if (B == 0) return RAGARC_OK;
+  RA_REQUIRE(x && mask && out, "pool_normalize: null pointer");
+  int threads = H >= 1024 ? 512 : (H >= 256 ? 256 : 128);
+  size_t smem = (threads / 32) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RAGARC_F32) pool_normalize_kernel<float><<<B, threads, smem, st>>>((const float*)x, mask, T, H, mode, normalize, out);
+  else if (dtype == RAGARC_BF16) pool_normalize_kernel<__nv_bfloat16><<<B, threads, smem, st>>>((const __nv_bfloat16*)x, mask, T, H, mode, normalize, out);
+  else if (dtype == RAGARC_F16) pool_normalize_kernel<__half><<<B, threads, smem, st>>>((const __half*)x, mask, T, H, mode, normalize, out);
+  else { set_error("pool_normalize: bad dtype %d", dtype); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_rrf_fuse(const int32_t* ids, int n_lists, int nq, int kl, double rrf_k, int top_k,
+                    int32_t* out_ids, double* out_scores, int32_t* out_count, void* stream) {
+  RA_REQUIRE(n_lists > 0 && nq >= 0 && kl > 0 && top_k > 0, "rrf_fuse: bad shape L=%d nq=%d kl=%d top_k=%d",
+             n_lists, nq, kl, top_k);
+  RA_REQUIRE((int64_t)n_lists * kl <= 4096, "rrf_fuse: L*kl=%d exceeds 4096", n_lists * kl);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(ids && out_ids && out_scores && out_count, "rrf_fuse: null pointer");
+  const int n = n_lists * kl;
+  size_t smem = (((size_t)n * 4 + 7) & ~(size_t)7) + (size_t)n * 8;
+  int threads = n <= 128 ? 128 : 256;
+  if (smem > 48 * 1024) RA_CUDA(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rrf_fuse_kernel<<<nq, threads, smem, (cudaStream_t)stream>>>(ids, n_lists, nq, kl, rrf_k, top_k, out_ids,
+                                                              out_scores, out_count);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_mmr_select(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
+                      const int64_t* cand_rows, int fetch_k, int k, double lambda_mult, int32_t* out_sel,
+                      void* stream) {
+  RA_REQUIRE(n > 0 && d > 0 && nq >= 0 && fetch_k > 0 && k > 0, "mmr_select: bad shape");
+  RA_REQUIRE(fetch_k <= 1024, "mmr_select: fetch_k=%d exceeds 1024", fetch_k);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(corpus && queries && cand_rows && out_sel, "mmr_select: null pointer");
+  size_t smem = (size_t)fetch_k * (3 * 8 + 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RAGARC_F32) mmr_select_kernel<float><<<nq, 256, smem, st>>>((const float*)corpus, d, (const float*)queries, cand_rows, fetch_k, k, lambda_mult, out_sel);
+  else if (dtype == RAGARC_BF16) mmr_select_kernel<__nv_bfloat16><<<nq, 256, smem, st>>>((const __nv_bfloat16*)corpus, d, (const __nv_bfloat16*)queries, cand_rows, fetch_k, k, lambda_mult, out_sel);
+  else if (dtype == RAGARC_F16) mmr_select_kernel<__half><<<nq, 256, smem, st>>>((const __half*)corpus, d, (const __half*)queries, cand_rows, fetch_k, k, lambda_mult, out_sel);
+  else { set_error("mmr_select: bad dtype %d", dtype); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+}  // extern "C"

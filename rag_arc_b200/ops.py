@@ -1,0 +1,221 @@
+"""Tensor-level entry points: torch CUDA tensors in, torch CUDA tensors out, every operation a
+call into the C ABI (``_native.lib``).  PyTorch is used for device buffers and streams only."""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_DT = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
+_ws_lock = threading.Lock()
+_ws_cache: dict = {}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dt}; use float32, bfloat16 or float16") from None
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise N.RagArcError(f"{name} must be a CUDA tensor: rag_arc_b200 has no CPU path")
+    if not t.is_contiguous():
+        raise N.RagArcError(f"{name} must be contiguous")
+    return t
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream, purpose); stream order makes reuse safe."""
+    key = (device.index, _stream_ptr(device), tag)
+    with _ws_lock:
+        buf = _ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            _ws_cache[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    with _ws_lock:
+        _ws_cache.clear()
+
+
+def normalize_cast(src: torch.Tensor, dtype: torch.dtype = torch.float32, normalize: bool = True,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [n,d] -> L2-normalised rows cast to ``dtype`` (faiss.normalize_L2 semantics)."""
+    _cuda(src, "src")
+    if src.dtype != torch.float32 or src.dim() != 2:
+        raise N.RagArcError("normalize_cast expects a 2-D float32 tensor")
+    n, d = src.shape
+    if out is None:
+        out = torch.empty((n, d), dtype=dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        N.check(N.lib.ragarc_normalize_cast(src.data_ptr(), out.data_ptr(), n, d, dtype_code(out.dtype),
+                                            int(bool(normalize)), _stream_ptr(src.device)), "normalize_cast")
+    return out
+
+
+def dense_workspace_bytes(n: int, d: int, dtype: torch.dtype, nq: int, k: int) -> int:
+    return int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, dtype_code(dtype), nq, k))
+
+
+def dense_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, n_rows: Optional[int] = None,
+               path: int = N.DENSE_AUTO, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               return_path: bool = False):
+    """Exact inner-product top-k of every query against rows ``[0, n_rows)`` of ``corpus``.
+
+    Returns ``(scores float32 [nq,k] descending, ids int64 [nq,k])``; ids are -1 (scores -inf)
+    past ``n_rows`` results.  Equal scores are ordered by ascending row id.
+    """
+    _cuda(corpus, "corpus"); _cuda(queries, "queries")
+    if corpus.dtype != queries.dtype:
+        raise N.RagArcError(f"corpus {corpus.dtype} and queries {queries.dtype} must share a dtype")
+    if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
+        raise N.RagArcError(f"shape mismatch: corpus {tuple(corpus.shape)} queries {tuple(queries.shape)}")
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    d = corpus.shape[1]
+    nq = queries.shape[0]
+    dev = corpus.device
+    if out is None:
+        scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    else:
+        scores, ids = out
+    code = dtype_code(corpus.dtype)
+    wsb = int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, code, nq, k))
+    ws = _workspace(dev, wsb, "dense")
+    used = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_dense_topk(corpus.data_ptr(), n, d, code, queries.data_ptr(), nq, k,
+                                        scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        path, ctypes.byref(used), _stream_ptr(dev)), "dense_topk")
+    if return_path:
+        return scores, ids, used.value
+    return scores, ids
+
+
+def dense_topk_keys(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base: int, *,
+                    n_rows: Optional[int] = None, path: int = N.DENSE_AUTO,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-shard search returning packed sortable keys (int64 view of uint64) for the all-gather."""
+    _cuda(corpus, "corpus"); _cuda(queries, "queries")
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    d = corpus.shape[1]
+    nq = queries.shape[0]
+    dev = corpus.device
+    keys = out if out is not None else torch.empty((nq, k), dtype=torch.int64, device=dev)
+    code = dtype_code(corpus.dtype)
+    ws = _workspace(dev, int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, code, nq, k)), "dense")
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_dense_topk_keys(corpus.data_ptr(), n, d, code, queries.data_ptr(), nq, k,
+                                             int(id_base), keys.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             path, None, _stream_ptr(dev)), "dense_topk_keys")
+    return keys
+
+
+def merge_topk_keys(keys: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """keys: [G, nq, k_in] packed keys (as all-gathered) -> merged (scores, ids)."""
+    _cuda(keys, "keys")
+    G, nq, k_in = keys.shape
+    dev = keys.device
+    scores = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_merge_topk_keys(keys.data_ptr(), G, nq, k_in, k_out, scores.data_ptr(),
+                                             ids.data_ptr(), _stream_ptr(dev)), "merge_topk_keys")
+    return scores, ids
+
+
+def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
+    """index: object with device tensors indptr/post_doc/post_tf/idf/doc_norm and k1_plus_1, n_docs."""
+    _cuda(q_terms, "q_terms"); _cuda(q_len, "q_len")
+    nq, tmax = q_terms.shape
+    dev = q_terms.device
+    scores = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    ws = _workspace(dev, int(N.lib.ragarc_bm25_workspace_bytes(index.n_docs, max(nq, 1))), "bm25")
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_bm25_topk(index.indptr.data_ptr(), index.post_doc.data_ptr(),
+                                       index.post_tf.data_ptr(), index.idf.data_ptr(),
+                                       index.doc_norm.data_ptr(), float(index.k1_plus_1),
+                                       q_terms.data_ptr(), q_len.data_ptr(), nq, tmax, index.n_docs, k,
+                                       scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(dev)), "bm25_topk")
+    return scores, ids
+
+
+def bm25_scores(index, q_terms: torch.Tensor, q_len: torch.Tensor) -> torch.Tensor:
+    _cuda(q_terms, "q_terms"); _cuda(q_len, "q_len")
+    nq, tmax = q_terms.shape
+    dev = q_terms.device
+    out = torch.empty((nq, index.n_docs), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_bm25_scores(index.indptr.data_ptr(), index.post_doc.data_ptr(),
+                                         index.post_tf.data_ptr(), index.idf.data_ptr(),
+                                         index.doc_norm.data_ptr(), float(index.k1_plus_1),
+                                         q_terms.data_ptr(), q_len.data_ptr(), nq, tmax, index.n_docs,
+                                         out.data_ptr(), _stream_ptr(dev)), "bm25_scores")
+    return out
+
+
+def rrf_fuse(ids: torch.Tensor, top_k: int, rrf_k: float = 60.0):
+    """ids: int32 [L, nq, kl] document keys (negative = padding).  Returns (ids int32 [nq,top_k],
+    scores float64 [nq,top_k], count int32 [nq])."""
+    _cuda(ids, "ids")
+    if ids.dtype != torch.int32 or ids.dim() != 3:
+        raise N.RagArcError("rrf_fuse expects int32 [L, nq, kl]")
+    L, nq, kl = ids.shape
+    dev = ids.device
+    out_ids = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+    out_scores = torch.empty((nq, top_k), dtype=torch.float64, device=dev)
+    out_count = torch.empty((nq,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_rrf_fuse(ids.data_ptr(), L, nq, kl, float(rrf_k), top_k, out_ids.data_ptr(),
+                                      out_scores.data_ptr(), out_count.data_ptr(), _stream_ptr(dev)),
+                "rrf_fuse")
+    return out_ids, out_scores, out_count
+
+
+_POOL = {"mean": N.POOL_MEAN, "cls": N.POOL_CLS, "last": N.POOL_LAST}
+
+
+def pool_normalize(x: torch.Tensor, mask: torch.Tensor, mode: str = "mean", normalize: bool = True
+                   ) -> torch.Tensor:
+    """x: [B,T,H] encoder output, mask: [B,T] (any integer/bool dtype) -> fp32 [B,H]."""
+    _cuda(x, "x")
+    if mode not in _POOL:
+        raise ValueError(f"pooling mode must be one of {sorted(_POOL)}")
+    B, T, H = x.shape
+    m = mask.to(device=x.device, dtype=torch.int32).contiguous()
+    out = torch.empty((B, H), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib.ragarc_pool_normalize(x.data_ptr(), dtype_code(x.dtype), m.data_ptr(), B, T, H,
+                                            _POOL[mode], int(bool(normalize)), out.data_ptr(),
+                                            _stream_ptr(x.device)), "pool_normalize")
+    return out
+
+
+def mmr_select(corpus: torch.Tensor, queries: torch.Tensor, cand_rows: torch.Tensor, k: int,
+               lambda_mult: float = 0.5, *, n_rows: Optional[int] = None) -> torch.Tensor:
+    """Greedy MMR over candidate rows [nq, fetch_k] (int64, -1 padded) -> int32 [nq,k] indices into
+    the candidate lists."""
+    _cuda(corpus, "corpus"); _cuda(queries, "queries"); _cuda(cand_rows, "cand_rows")
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    nq, fetch_k = cand_rows.shape
+    out = torch.empty((nq, k), dtype=torch.int32, device=corpus.device)
+    with torch.cuda.device(corpus.device):
+        N.check(N.lib.ragarc_mmr_select(corpus.data_ptr(), n, corpus.shape[1], dtype_code(corpus.dtype),
+                                        queries.data_ptr(), nq, cand_rows.data_ptr(), fetch_k, k,
+                                        float(lambda_mult), out.data_ptr(), _stream_ptr(corpus.device)),
+                "mmr_select")
+    return out

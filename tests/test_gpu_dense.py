@@ -1,0 +1,168 @@
+"""GPU parity: fused dense scoring + top-k (C ABI ``ragarc_dense_topk``) against the oracle
+restatement of ``faiss.IndexFlatIP.search`` (VectorStore_Faiss.py:263) on identical inputs.
+
+Tolerances: both sides consume the same storage-dtype values, both accumulate in fp32, so scores
+must agree within 1e-5 * max(1,|s|) (north_star: "1e-5 for fp32 accumulate"); ids must agree
+except inside groups of scores closer than that (tie-aware comparator).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense as odense
+from oracle.compare import check_topk_against_scores
+from rag_arc_b200 import _native as N
+from rag_arc_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _check_all(ids, scores, X, Q, k, what):
+    S = Q.astype(np.float64) @ X.astype(np.float64).T
+    ids = ids.cpu().numpy(); scores = scores.cpu().numpy()
+    for i in range(Q.shape[0]):
+        check_topk_against_scores(ids[i], scores[i], S[i], k, rtol=RTOL, atol=ATOL, what=f"{what} q{i}")
+
+
+def test_c1_fp32_flat_ip_matches_faiss_restatement(dev):
+    """BASELINE config 1: 10k x 384 normalised fp32, 100 queries, top-10."""
+    X = synth.dense_corpus_np(10_000, 384)
+    Q, planted = synth.dense_queries_np(X, 100)
+    D, I = odense.flat_ip_search(X, Q, 10)
+    scores, ids, path = ops.dense_topk(torch.from_numpy(X).to(dev), torch.from_numpy(Q).to(dev), 10,
+                                       return_path=True)
+    assert path == N.DENSE_SIMT
+    assert (ids.cpu().numpy() == I).all()
+    assert np.allclose(scores.cpu().numpy(), D, rtol=RTOL, atol=ATOL)
+    assert (ids[:, 0].cpu().numpy() == planted).all()
+    _check_all(ids, scores, X, Q, 10, "c1")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 64, 7, 5), (33_000, 768, 130, 100), (70_001, 384, 256, 50),
+                                      (1000, 1024, 1, 10), (257, 72, 3, 200)])
+def test_tcgen05_path_matches_oracle(dev, dtype, n, d, nq, k):
+    x = synth.dense_corpus_cuda(n, d, dtype, dev, seed=7)
+    q, planted = synth.dense_queries_cuda(x, nq, seed=11)
+    scores, ids, path = ops.dense_topk(x, q, k, return_path=True)
+    assert path == N.DENSE_TCGEN05
+    X = x.float().cpu().numpy(); Q = q.float().cpu().numpy()
+    _check_all(ids, scores, X, Q, k, f"tc {dtype} {n}x{d}")
+    assert (ids[:, 0].cpu() == planted.cpu()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simt_and_tc_agree_bitwise_on_ids(dev, dtype):
+    """Same bf16 inputs through both kernels: identical ids, scores within fp32 summation noise."""
+    n, d, nq, k = 20_000, 256, 64, 20
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=3).to(dtype)
+    q, _ = synth.dense_queries_cuda(x, nq, seed=5)
+    s1, i1 = ops.dense_topk(x, q, k, path=N.DENSE_SIMT)
+    if dtype == torch.float32:
+        _check_all(i1, s1, x.cpu().numpy(), q.cpu().numpy(), k, "simt f32")
+        return
+    s2, i2 = ops.dense_topk(x, q, k, path=N.DENSE_TCGEN05)
+    assert torch.allclose(s1, s2, rtol=RTOL, atol=ATOL)
+    X = x.float().cpu().numpy(); Q = q.float().cpu().numpy()
+    _check_all(i1, s1, X, Q, k, "simt bf16")
+    _check_all(i2, s2, X, Q, k, "tc bf16")
+
+
+def test_k_larger_than_corpus_pads_with_minus_one(dev):
+    x = synth.dense_corpus_cuda(37, 64, torch.bfloat16, dev)
+    q, _ = synth.dense_queries_cuda(x, 4)
+    for path in (N.DENSE_SIMT, N.DENSE_TCGEN05):
+        scores, ids = ops.dense_topk(x, q, 50, path=path)
+        ids = ids.cpu().numpy(); scores = scores.cpu().numpy()
+        assert (ids[:, 37:] == -1).all() and np.isinf(scores[:, 37:]).all()
+        for i in range(4):
+            assert sorted(ids[i, :37].tolist()) == list(range(37))
+            assert (np.diff(scores[i, :37]) <= 0).all()
+
+
+def test_ties_resolve_to_lowest_row_id(dev):
+    """Duplicate rows give exactly equal scores; the lowest row id must come first, and a zero
+    query (all scores equal) must return rows 0..k-1."""
+    base = synth.dense_corpus_cuda(500, 128, torch.bfloat16, dev, seed=1)
+    x = torch.cat([base, base, base], dim=0).contiguous()        # rows r, r+500, r+1000 identical
+    q, planted = synth.dense_queries_cuda(base, 9, seed=2)
+    q = torch.cat([q, torch.zeros((1, 128), dtype=q.dtype, device=dev)], dim=0).contiguous()
+    for path in (N.DENSE_SIMT, N.DENSE_TCGEN05):
+        scores, ids = ops.dense_topk(x, q, 6, path=path)
+        ids = ids.cpu().numpy(); scores = scores.cpu().numpy()
+        for i in range(9):
+            p = int(planted[i])
+            assert ids[i, :3].tolist() == [p, p + 500, p + 1000]
+            assert scores[i, 0] == scores[i, 1] == scores[i, 2]
+            r = ids[i, 3]
+            assert ids[i, 3:6].tolist() == [r, r + 500, r + 1000]
+        assert ids[9].tolist() == [0, 1, 2, 3, 4, 5] and (scores[9] == 0).all()
+
+
+def test_ascending_scores_worst_case_for_running_threshold(dev):
+    """Rows ordered so that every later row scores higher: the running threshold never helps and
+    every list must be pruned again and again; result must still be exact."""
+    n, d, k = 6000, 64, 10
+    x = torch.zeros((n, d), dtype=torch.float32)
+    x[:, 0] = torch.linspace(0.001, 1.0, n)
+    x[:, 1] = 0.25
+    x = x.to(torch.bfloat16).to(dev)
+    q = torch.zeros((3, d), dtype=torch.bfloat16, device=dev)
+    q[:, 0] = 1.0
+    for path in (N.DENSE_SIMT, N.DENSE_TCGEN05):
+        scores, ids = ops.dense_topk(x, q, k, path=path)
+        _check_all(ids, scores, x.float().cpu().numpy(), q.float().cpu().numpy(), k, "ascending")
+
+
+def test_rows_subset_and_result_independent_of_it(dev):
+    """``n_rows`` < allocated rows (the store keeps spare capacity): rows past it are ignored."""
+    x = synth.dense_corpus_cuda(4096, 128, torch.bfloat16, dev, seed=9)
+    q, _ = synth.dense_queries_cuda(x, 5, seed=10, n_rows=1000)
+    s_a, i_a = ops.dense_topk(x, q, 8, n_rows=1000)
+    s_b, i_b = ops.dense_topk(x[:1000].contiguous(), q, 8)
+    assert torch.equal(i_a, i_b) and torch.equal(s_a, s_b)
+    assert int(i_a.max()) < 1000
+
+
+def test_keys_and_merge_equal_single_shot(dev):
+    """Shard the corpus in 3 uneven pieces, search each, merge the packed keys: must be bitwise the
+    single-shot result (the multi-GPU path's arithmetic, on one device)."""
+    n, d, nq, k = 50_000, 128, 33, 20
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=21)
+    q, _ = synth.dense_queries_cuda(x, nq, seed=22)
+    s_ref, i_ref = ops.dense_topk(x, q, k)
+    cuts = [0, 17_000, 17_100, n]
+    keys = [ops.dense_topk_keys(x[a:b].contiguous(), q, k, id_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    s, i = ops.merge_topk_keys(torch.stack(keys, 0).contiguous(), k)
+    assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
+
+
+def test_full_size_properties_1m_x_768(dev):
+    """BASELINE config 3 at full size (1M x 768 bf16, 1024 queries, top-100) through
+    size-independent properties: planted neighbour at rank 1, scores descending, ids unique and
+    in range, every returned score equals the recomputed fp32 dot product, and nothing in a
+    random 20k-row sample beats the k-th score."""
+    n, d, nq, k = 1_000_000, 768, 1024, 100
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev)
+    q, planted = synth.dense_queries_cuda(x, nq)
+    scores, ids, path = ops.dense_topk(x, q, k, return_path=True)
+    assert path == N.DENSE_TCGEN05
+    assert (ids[:, 0] == planted).all()
+    assert (scores[:, 1:] <= scores[:, :-1]).all()
+    assert int(ids.min()) >= 0 and int(ids.max()) < n
+    srt = ids.sort(dim=1).values
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    for i in range(0, nq, 64):
+        rec = (x[ids[i]].float() @ q[i].float())
+        assert torch.allclose(rec, scores[i], rtol=1e-5, atol=1e-5)
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    sample = torch.randint(0, n, (20_000,), generator=g, device=dev)
+    S = q.float() @ x[sample].float().T                    # [nq, 20000]
+    kth = scores[:, -1:]
+    beats = S > kth + 1e-5
+    # any sampled row that beats the k-th score must already be in the result
+    rows_q, cols = beats.nonzero(as_tuple=True)
+    for rq, c in zip(rows_q.tolist()[:2000], cols.tolist()[:2000]):
+        assert (ids[rq] == sample[c]).any()
