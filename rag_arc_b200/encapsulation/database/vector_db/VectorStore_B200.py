@@ -1,0 +1,329 @@
+"""``B200VectorStore``: drop-in for ``FaissVectorStore`` (/root/reference
+encapsulation/database/vector_db/VectorStore_Faiss.py) whose index lives in B200 HBM.
+
+Same constructor arguments, attributes (``embedding``, ``index``, ``index_type``, ``metric``,
+``normalize_L2``, ``docstore``, ``index_to_docstore_id``), methods, return types and errors as the
+reference class (:68-513).  What changes underneath:
+
+* the corpus is one contiguous row-major ``[capacity, d]`` device matrix (fp32 by default - the
+  reference's precision - or bf16/fp16 via ``dtype=`` for the tensor-core path), rows appended at
+  ``ntotal`` exactly like ``IndexFlatIP.add`` (:199-208);
+* ``faiss.normalize_L2`` (:150-154) and the fp32 staging casts (:170,:258) are
+  ``ragarc_normalize_cast``; ``IndexFlatIP.search`` (:263) is ``ragarc_dense_topk`` (scoring fused
+  with per-query top-k);
+* MMR gathers candidate rows from the resident matrix instead of re-embedding every candidate
+  (:301-304) and runs ``ragarc_mmr_select``;
+* ``delete`` compacts rows on the device instead of re-embedding the survivors (:374-415);
+* batched entry points (``search_batch``, ``similarity_search_batch``) sit next to the
+  single-query methods - the reference has none.
+
+Only exact ("flat") search is offered; ``index_type`` "ivf"/"hnsw" (approximate in the
+reference) and metric "l2" raise ``ValueError``.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import uuid
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ....core.utils.data_model import Document
+from .... import ops
+from .VectorStoreBase import VectorStore
+
+_DTYPES = {"float32": torch.float32, "fp32": torch.float32, "bfloat16": torch.bfloat16, "bf16": torch.bfloat16,
+           "float16": torch.float16, "fp16": torch.float16}
+
+
+def _as_dtype(dt) -> torch.dtype:
+    if isinstance(dt, torch.dtype):
+        if dt not in ops._DT:
+            raise ValueError(f"unsupported storage dtype: {dt}")
+        return dt
+    try:
+        return _DTYPES[str(dt).lower()]
+    except KeyError:
+        raise ValueError(f"unsupported storage dtype: {dt}") from None
+
+
+class FlatIndexB200:
+    """The slice of the ``faiss.IndexFlatIP`` API the reference uses (``d``, ``ntotal``,
+    ``is_trained``, ``add``, ``reset``, ``search``) over a device-resident matrix."""
+
+    def __init__(self, d: int, dtype: torch.dtype, device, normalize: bool):
+        self.d = int(d)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.normalize = normalize
+        self.is_trained = True
+        self.ntotal = 0
+        self.rows = torch.empty((0, self.d), dtype=dtype, device=self.device)
+
+    def _reserve(self, need: int) -> None:
+        cap = self.rows.shape[0]
+        if need <= cap:
+            return
+        new_cap = max(need, int(cap * 1.5) + 1024)
+        grown = torch.empty((new_cap, self.d), dtype=self.dtype, device=self.device)
+        if self.ntotal:
+            grown[:self.ntotal].copy_(self.rows[:self.ntotal])
+        self.rows = grown
+
+    def add(self, x) -> None:
+        """x: fp32 [n,d] numpy array or tensor (host or device); normalised (if the store's metric
+        asks for it) and cast into the matrix on the device."""
+        xt = torch.as_tensor(x)
+        if xt.dim() != 2 or xt.shape[1] != self.d:
+            raise ValueError(f"expected [n,{self.d}] vectors, got {tuple(xt.shape)}")
+        xt = xt.to(device=self.device, dtype=torch.float32).contiguous()
+        n = xt.shape[0]
+        self._reserve(self.ntotal + n)
+        ops.normalize_cast(xt, self.dtype, self.normalize, out=self.rows[self.ntotal:self.ntotal + n])
+        self.ntotal += n
+
+    def add_prepared(self, rows: torch.Tensor) -> None:
+        """Append rows that are already normalised and in the storage dtype (device tensor)."""
+        n = rows.shape[0]
+        self._reserve(self.ntotal + n)
+        self.rows[self.ntotal:self.ntotal + n].copy_(rows)
+        self.ntotal += n
+
+    def reset(self) -> None:
+        self.ntotal = 0
+
+    def prepare_queries(self, q) -> torch.Tensor:
+        qt = torch.as_tensor(q)
+        if qt.dim() == 1:
+            qt = qt[None, :]
+        qt = qt.to(device=self.device, dtype=torch.float32).contiguous()
+        return ops.normalize_cast(qt, self.dtype, self.normalize)
+
+    def search_device(self, q_prepared: torch.Tensor, k: int):
+        return ops.dense_topk(self.rows, q_prepared, k, n_rows=self.ntotal)
+
+    def search(self, q, k: int):
+        """faiss-style: numpy in, ``(D float32 [nq,k], I int64 [nq,k])`` numpy out."""
+        D, I = self.search_device(self.prepare_queries(q), k)
+        return D.cpu().numpy(), I.cpu().numpy()
+
+
+class B200VectorStore(VectorStore):
+    def __init__(self, embedding, index: Optional[FlatIndexB200] = None, index_type: str = "flat",
+                 metric: str = "cosine", normalize_L2: bool = False, dtype="float32", device="cuda",
+                 **kwargs: Any):
+        super().__init__(**kwargs)
+        self.embedding = embedding
+        self.index_type = index_type
+        self.metric = metric
+        self.normalize_L2 = normalize_L2
+        self.index = index
+        self.dtype = _as_dtype(dtype)
+        self.device = torch.device(device)
+        self.docstore: dict[str, Document] = {}
+        self.index_to_docstore_id: dict[int, str] = {}
+
+    # ---- index management --------------------------------------------------------------------
+    def _get_dimension(self) -> int:
+        if self.index is not None:
+            return self.index.d
+        return len(self.embedding.embed_query("test"))
+
+    def _create_index(self, dimension: int) -> FlatIndexB200:
+        if self.metric not in ("cosine", "ip", "l2"):
+            raise ValueError(f"unsupported metric: {self.metric}")
+        if self.index_type != "flat":
+            raise ValueError(f"unsupported index type: {self.index_type} (B200VectorStore is exact/flat only)")
+        if self.metric == "l2":
+            raise ValueError("metric 'l2' is not offered by B200VectorStore (inner product / cosine only)")
+        return FlatIndexB200(dimension, self.dtype, self.device, self._normalizes())
+
+    def _normalizes(self) -> bool:
+        return bool(self.normalize_L2 or self.metric == "cosine")
+
+    @property
+    def ntotal(self) -> int:
+        return 0 if self.index is None else self.index.ntotal
+
+    def add_texts(self, texts: List[str], metadatas: Optional[List[dict]] = None, *,
+                  ids: Optional[List[str]] = None, **kwargs: Any) -> List[str]:
+        texts = list(texts)
+        if not texts:
+            return []
+        vectors = np.asarray(self.embedding.embed_documents(texts), dtype=np.float32)
+        return self.add_embeddings(texts, vectors, metadatas, ids=ids)
+
+    def add_embeddings(self, texts: Sequence[str], vectors, metadatas: Optional[List[dict]] = None, *,
+                       ids: Optional[List[str]] = None) -> List[str]:
+        """Append pre-computed embeddings (fp32 ``[n,d]`` numpy or tensor, host or device)."""
+        texts = list(texts)
+        if self.index is None:
+            self.index = self._create_index(int(vectors.shape[1]))
+        if ids is None:
+            ids = [str(uuid.uuid4()) for _ in texts]
+        elif len(ids) != len(texts):
+            raise ValueError("number of ids must match number of texts")
+        if metadatas is None:
+            metadatas = [{} for _ in texts]
+        elif len(metadatas) != len(texts):
+            raise ValueError("number of metadatas must match number of texts")
+        start = self.index.ntotal
+        self.index.add(vectors)
+        for i, (text, meta, doc_id) in enumerate(zip(texts, metadatas, ids)):
+            self.docstore[doc_id] = Document(content=text, metadata=meta, id=doc_id)
+            self.index_to_docstore_id[start + i] = doc_id
+        return list(ids)
+
+    # ---- search ------------------------------------------------------------------------------
+    def similarity_search(self, query: str, k: int = 4, **kwargs: Any) -> List[Document]:
+        return [doc for doc, _ in self.similarity_search_with_score(query, k, **kwargs)]
+
+    def similarity_search_with_score(self, query: str, k: int = 4, **kwargs: Any) -> List[Tuple[Document, float]]:
+        if self.ntotal == 0:
+            return []
+        return self.similarity_search_by_vector_with_score(self.embedding.embed_query(query), k, **kwargs)
+
+    def similarity_search_by_vector(self, embedding: List[float], k: int = 4, **kwargs: Any) -> List[Document]:
+        return [doc for doc, _ in self.similarity_search_by_vector_with_score(embedding, k, **kwargs)]
+
+    def similarity_search_by_vector_with_score(self, embedding: List[float], k: int = 4, **kwargs: Any
+                                               ) -> List[Tuple[Document, float]]:
+        if self.ntotal == 0:
+            return []
+        k = min(k, self.ntotal)
+        D, I = self.index.search(np.asarray([embedding], dtype=np.float32), k)
+        out = []
+        for score, row in zip(D[0], I[0]):
+            if row == -1:
+                continue
+            out.append((self.docstore[self.index_to_docstore_id[int(row)]], float(score)))
+        return out
+
+    def search_batch(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Batched search: ``queries`` fp32 ``[nq,d]`` (numpy / host tensor / device tensor) ->
+        device tensors ``(scores float32 [nq,k], rows int64 [nq,k])``; -1 rows pad when k > ntotal."""
+        if self.index is None:
+            raise ValueError("the store is empty")
+        return self.index.search_device(self.index.prepare_queries(queries), k)
+
+    def similarity_search_batch(self, queries: List[str], k: int = 4) -> List[List[Tuple[Document, float]]]:
+        if self.ntotal == 0:
+            return [[] for _ in queries]
+        vecs = np.asarray(self.embedding.embed_documents(list(queries)), dtype=np.float32)
+        D, I = self.search_batch(vecs, min(k, self.ntotal))
+        D = D.cpu().numpy(); I = I.cpu().numpy()
+        return [[(self.docstore[self.index_to_docstore_id[int(r)]], float(s)) for s, r in zip(Dq, Iq) if r != -1]
+                for Dq, Iq in zip(D, I)]
+
+    def rows_to_documents(self, rows: Sequence[int]) -> List[Document]:
+        return [self.docstore[self.index_to_docstore_id[int(r)]] for r in rows if r != -1]
+
+    # ---- maximal marginal relevance --------------------------------------------------------------
+    def max_marginal_relevance_search(self, query: str, k: int = 4, fetch_k: int = 20,
+                                      lambda_mult: float = 0.5, **kwargs: Any) -> List[Document]:
+        if self.ntotal == 0:
+            return []
+        return self.max_marginal_relevance_search_by_vector(self.embedding.embed_query(query), k, fetch_k,
+                                                            lambda_mult, **kwargs)
+
+    def max_marginal_relevance_search_by_vector(self, embedding: List[float], k: int = 4, fetch_k: int = 20,
+                                                lambda_mult: float = 0.5, **kwargs: Any) -> List[Document]:
+        if self.ntotal == 0:
+            return []
+        fetch = min(fetch_k, self.ntotal)
+        q = self.index.prepare_queries(np.asarray([embedding], dtype=np.float32))
+        _, cand = self.index.search_device(q, fetch)
+        if k >= fetch:
+            return self.rows_to_documents(cand[0].tolist())
+        sel = ops.mmr_select(self.index.rows, q, cand.contiguous(), k, lambda_mult, n_rows=self.ntotal)
+        cand_h = cand[0].tolist()
+        return self.rows_to_documents([cand_h[j] for j in sel[0].tolist() if j >= 0])
+
+    # ---- maintenance ---------------------------------------------------------------------------
+    def delete(self, ids: Optional[List[str]] = None, **kwargs: Any) -> Optional[bool]:
+        if ids is None:
+            self.docstore.clear()
+            self.index_to_docstore_id.clear()
+            if self.index is not None:
+                self.index.reset()
+            return True
+        if not ids:
+            return True
+        for doc_id in ids:
+            if doc_id not in self.docstore:
+                return False
+        drop = set(ids)
+        row_of = {doc_id: row for row, doc_id in self.index_to_docstore_id.items()}
+        keep_ids = [doc_id for doc_id in self.docstore if doc_id not in drop]
+        keep_rows = torch.tensor([row_of[d] for d in keep_ids], dtype=torch.int64, device=self.device)
+        survivors = self.index.rows.index_select(0, keep_rows) if keep_ids else None
+        kept_docs = [self.docstore[d] for d in keep_ids]
+        self.docstore.clear()
+        self.index_to_docstore_id.clear()
+        self.index.reset()
+        if keep_ids:
+            self.index.add_prepared(survivors)
+            for row, doc in enumerate(kept_docs):
+                self.docstore[doc.id] = doc
+                self.index_to_docstore_id[row] = doc.id
+        return True
+
+    def get_by_ids(self, ids: Sequence[str], /) -> List[Document]:
+        return [self.docstore[i] for i in ids if i in self.docstore]
+
+    def _select_relevance_score_fn(self) -> Callable[[float], float]:
+        if self.metric == "cosine" or self.normalize_L2:
+            return self._cosine_relevance_score_fn
+        if self.metric == "l2":
+            return self._euclidean_relevance_score_fn
+        if self.metric == "ip":
+            return self._max_inner_product_relevance_score_fn
+        raise ValueError(f"unsupported metric: {self.metric}")
+
+    # ---- persistence -----------------------------------------------------------------------------
+    def save_local(self, folder_path: str, index_name: str = "index") -> None:
+        """``<name>.b200.npy`` (the row matrix; bf16 stored as its uint16 bit pattern) +
+        ``<name>.pkl`` with the same sidecar keys the reference pickles (:441-450) plus the dtype."""
+        os.makedirs(folder_path, exist_ok=True)
+        if self.index is not None:
+            rows = self.index.rows[:self.index.ntotal]
+            host = (rows.view(torch.int16) if self.dtype == torch.bfloat16 else rows).cpu().numpy()
+            np.save(os.path.join(folder_path, f"{index_name}.b200.npy"), host)
+        side = {"docstore": self.docstore, "index_to_docstore_id": self.index_to_docstore_id,
+                "index_type": self.index_type, "metric": self.metric, "normalize_L2": self.normalize_L2,
+                "dtype": str(self.dtype).replace("torch.", "")}
+        with open(os.path.join(folder_path, f"{index_name}.pkl"), "wb") as fh:
+            pickle.dump(side, fh)
+
+    @classmethod
+    def load_local(cls, folder_path: str, embeddings, index_name: str = "index", **kwargs: Any) -> "B200VectorStore":
+        with open(os.path.join(folder_path, f"{index_name}.pkl"), "rb") as fh:
+            side = pickle.load(fh)
+        store = cls(embedding=embeddings, index_type=side["index_type"], metric=side["metric"],
+                    normalize_L2=side["normalize_L2"], dtype=side.get("dtype", "float32"), **kwargs)
+        path = os.path.join(folder_path, f"{index_name}.b200.npy")
+        if os.path.exists(path):
+            host = torch.from_numpy(np.load(path))
+            if store.dtype == torch.bfloat16:
+                host = host.view(torch.bfloat16)
+            store.index = store._create_index(int(host.shape[1]))
+            store.index.add_prepared(host.to(store.device))
+        store.docstore = side["docstore"]
+        store.index_to_docstore_id = side["index_to_docstore_id"]
+        return store
+
+    @classmethod
+    def from_texts(cls, texts: List[str], embedding, metadatas: Optional[List[dict]] = None, *,
+                   ids: Optional[List[str]] = None, **kwargs: Any) -> "B200VectorStore":
+        store = cls(embedding=embedding, **kwargs)
+        store.add_texts(texts, metadatas=metadatas, ids=ids)
+        return store
+
+    @classmethod
+    def from_embeddings(cls, texts: Sequence[str], vectors, embedding=None, metadatas=None, *, ids=None,
+                        **kwargs: Any) -> "B200VectorStore":
+        store = cls(embedding=embedding, **kwargs)
+        store.add_embeddings(texts, vectors, metadatas, ids=ids)
+        return store
