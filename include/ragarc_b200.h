@@ -54,6 +54,15 @@ const char* ragarc_last_error(void);
  * threads).  bench.py reports the delta over its timed region as "gpu_launches". */
 uint64_t ragarc_launch_count(void);
 
+/* Measurement hooks (bench.py): when enabled, every dense search records CUDA events on the
+ * caller's stream around its three phases: threshold seeding (tcgen05 path on large corpora
+ * only, else ~0), the main scoring + selection kernel, and the merge kernel.
+ * ragarc_profile_read synchronises on the recorded events, returns the summed device times in
+ * milliseconds and the number of searches recorded since the last read, and clears the record. */
+int ragarc_profile_enable(int on);
+int ragarc_profile_read(double* seed_ms_sum_host, double* score_ms_sum_host,
+                        double* merge_ms_sum_host, int* n_host);
+
 /* ---------------------------------------------------------------------------------------------
  * L2 normalise + cast.   Replaces faiss.normalize_L2 at
  *   encapsulation/database/vector_db/VectorStore_Faiss.py:150-154 (called :178 on add, :259 on

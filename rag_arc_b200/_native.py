@@ -22,7 +22,8 @@ DENSE_AUTO, DENSE_SIMT, DENSE_TCGEN05 = 0, 1, 2
 
 # every symbol include/ragarc_b200.h declares (tests/test_abi.py checks the two stay in sync)
 EXPORTS = [
-    "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_normalize_cast",
+    "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
+    "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk", "ragarc_dense_topk_keys",
     "ragarc_merge_topk_keys", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
@@ -64,6 +65,9 @@ def _load():
         "ragarc_abi_version": (c_int, []),
         "ragarc_last_error": (ctypes.c_char_p, []),
         "ragarc_launch_count": (c_uint64, []),
+        "ragarc_profile_enable": (c_int, [c_int]),
+        "ragarc_profile_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_double),
+                                        ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
         "ragarc_normalize_cast": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
         "ragarc_dense_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
         "ragarc_dense_topk": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, P, P, P, c_size_t,
@@ -99,6 +103,18 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib.ragarc_last_error().decode("utf-8", "replace")
         raise RagArcError(f"{what or 'ragarc'} failed (code {rc}): {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib.ragarc_profile_enable(int(bool(on))), "profile_enable")
+
+
+def profile_read():
+    """-> (seed ms, scoring kernel ms, merge kernel ms - each summed - and the number of searches)."""
+    s, a, b, n = c_double(0), c_double(0), c_double(0), c_int(0)
+    check(lib.ragarc_profile_read(ctypes.byref(s), ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)),
+          "profile_read")
+    return s.value, a.value, b.value, n.value
 
 
 def launch_count() -> int:

@@ -1,0 +1,135 @@
+"""``MultiPathRetriever`` (drop-in for /root/reference core/retrieval/mutipath.py).
+
+Single-query path identical in behaviour to the reference (:37-93): retrievers are invoked in
+order with ``k = top_k_per_retriever`` forced (other kwargs, ``top_k`` included, are forwarded),
+a retriever that raises contributes an empty list and a printed message (:78-80), all-empty gives
+``[]`` (:83-84), results are wrapped as ``RetrievalResult(rank=i+1)`` and fused with
+``fusion_method.fuse(all_results, top_k)`` (``top_k`` default 10, :56), documents only are returned.
+
+``invoke_batch`` is the B200 addition: every retriever that can answer a whole query batch on
+the device (``batch_rows``) does so, rows are translated to content-canonical integer keys with a
+device lookup table and the whole batch is fused by one ``ragarc_rrf_fuse`` launch.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ..utils.data_model import Document
+from ..utils.Fusion import FusionMethod, RetrievalResult, RRFusion
+from .base import BaseRetriever
+
+
+class MultiPathRetriever(BaseRetriever):
+    def __init__(self, retrievers: List[BaseRetriever], fusion_method: Optional[FusionMethod] = None,
+                 top_k_per_retriever: int = 50):
+        self.retrievers = retrievers
+        self.fusion_method = fusion_method or RRFusion()
+        self.top_k_per_retriever = top_k_per_retriever
+        self._canon_cache = None
+
+    def _get_relevant_documents(self, query: str, **kwargs: Any) -> List[Document]:
+        top_k = kwargs.get("top_k", 10)
+        all_results: List[List[RetrievalResult]] = []
+        for retriever in self.retrievers:
+            try:
+                docs = retriever.invoke(query, **{**kwargs, "k": self.top_k_per_retriever})
+                all_results.append([RetrievalResult(document=d, score=getattr(d, "score", 1.0), rank=i + 1)
+                                    for i, d in enumerate(docs)])
+            except Exception as exc:  # noqa: BLE001 - reference behaviour: swallow, report, continue
+                print(f"retriever {type(retriever).__name__} failed: {exc}")
+                all_results.append([])
+        if not all_results or all(len(r) == 0 for r in all_results):
+            return []
+        return [r.document for r in self.fusion_method.fuse(all_results, top_k)]
+
+    # ---- batched hybrid (B200 addition) ------------------------------------------------------------
+    def _canonical_tables(self, device):
+        """content -> integer key (first appearance over the retrievers, in order) and, per
+        retriever, a device table row -> key.  Rebuilt when a retriever's corpus size changes."""
+        sig = tuple(len(r.row_documents()) for r in self.retrievers)
+        if self._canon_cache is not None and self._canon_cache[0] == sig:
+            return self._canon_cache[1], self._canon_cache[2]
+        keys: Dict[str, int] = {}
+        tables = []
+        for r in self.retrievers:
+            docs = r.row_documents()
+            tab = np.fromiter((keys.setdefault(d.content, len(keys)) for d in docs), np.int32, len(docs))
+            tables.append(torch.from_numpy(tab).to(device))
+        self._canon_cache = (sig, keys, tables)
+        return keys, tables
+
+    def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
+        top_k = kwargs.get("top_k", 10)
+        if not all(hasattr(r, "batch_rows") for r in self.retrievers) or not isinstance(self.fusion_method, RRFusion):
+            return [self.invoke(q, **kwargs) for q in queries]
+        kl = self.top_k_per_retriever
+        device = torch.device(getattr(self.fusion_method, "device", "cuda"))
+        _, tables = self._canonical_tables(device)
+        nq = len(queries)
+        ids = torch.full((len(self.retrievers), nq, kl), -1, dtype=torch.int32, device=device)
+        for l, r in enumerate(self.retrievers):
+            try:
+                if len(r.row_documents()) == 0:
+                    continue
+                rows = r.batch_rows(queries, kl).to(device)
+                valid = rows >= 0
+                keys = tables[l][rows.clamp(min=0)]
+                ids[l, :, :rows.shape[1]] = torch.where(valid, keys, torch.full_like(keys, -1))
+            except Exception as exc:  # noqa: BLE001
+                print(f"retriever {type(r).__name__} failed: {exc}")
+        fused_ids, _, counts = self.fusion_method.fuse_batch(ids.contiguous(), top_k)
+        fused_ids = fused_ids.cpu().numpy(); counts = counts.cpu().numpy(); ids_h = ids.cpu().numpy()
+        rows_h = None
+        out: List[List[Document]] = []
+        # reference semantics: the Document returned for a content string is the LAST one seen
+        # while walking the lists in retriever order (Fusion.py:61)
+        row_docs = [r.row_documents() for r in self.retrievers]
+        key_to_row = []
+        for l in range(len(self.retrievers)):
+            tab = tables[l].cpu().numpy()
+            first = {}
+            for row, key in enumerate(tab.tolist()):
+                first.setdefault(key, []).append(row)
+            key_to_row.append(first)
+        del rows_h
+        for q in range(nq):
+            docs = []
+            for key in fused_ids[q, :counts[q]].tolist():
+                doc = None
+                for l in range(len(self.retrievers) - 1, -1, -1):
+                    pos = np.nonzero(ids_h[l, q] == key)[0]
+                    if len(pos):
+                        # the document object this retriever returned at its LAST position for this
+                        # key; several rows can share a content string, recover the row from the
+                        # retriever's own ranking order
+                        doc = self._doc_for(l, q, int(pos[-1]), key, key_to_row[l], row_docs[l])
+                        break
+                docs.append(doc)
+            out.append(docs)
+        return out
+
+    def _doc_for(self, l, q, pos, key, key_rows, docs):
+        rows = key_rows.get(key, [])
+        if len(rows) == 1:
+            return docs[rows[0]]
+        # ambiguous (duplicate content inside one retriever's corpus): any of them carries the same
+        # content; prefer the last row, matching "last one seen" for equal-score duplicates
+        return docs[rows[-1]] if rows else None
+
+    # ---- management --------------------------------------------------------------------------------
+    def add_retriever(self, retriever: BaseRetriever):
+        self.retrievers.append(retriever)
+        self._canon_cache = None
+
+    def remove_retriever(self, name: str):
+        for i, r in enumerate(self.retrievers):
+            if type(r).__name__ == name:
+                self.retrievers.pop(i)
+                break
+        self._canon_cache = None
+
+    def set_fusion_method(self, fusion_method: FusionMethod):
+        self.fusion_method = fusion_method

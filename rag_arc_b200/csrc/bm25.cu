@@ -104,14 +104,13 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
   for (int pass = 0; pass < 12 && kk > 0; ++pass) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
-      const uint64_t o = f64_to_ord(acc[i]);
+    for (int64_t b = 0; b < n_docs; b += blockDim.x) {
+      const int64_t i = b + threadIdx.x;
+      const uint64_t o = i < n_docs ? f64_to_ord(acc[i]) : 0ull;
       const uint32_t nid = ~(uint32_t)i;
-      if ((o & mask_hi) == pre_hi && (nid & mask_lo) == pre_lo) {
-        const uint32_t dig = pass < 8 ? (uint32_t)(o >> (56 - 8 * pass)) & 0xFFu
-                                      : (nid >> (24 - 8 * (pass - 8))) & 0xFFu;
-        atomicAdd(&hist[dig], 1u);
-      }
+      const uint32_t dig = pass < 8 ? (uint32_t)(o >> (56 - 8 * pass)) & 0xFFu
+                                    : (nid >> (24 - 8 * (pass - 8))) & 0xFFu;
+      hist_add_agg(hist, dig, i < n_docs && (o & mask_hi) == pre_hi && (nid & mask_lo) == pre_lo);
     }
     __syncthreads();
     if (threadIdx.x < 32) find_bucket(hist, rem, sel);

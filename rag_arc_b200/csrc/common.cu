@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace ragarc {
@@ -27,6 +29,11 @@ int sm_count() {
   cached = n;
   return n;
 }
+
+struct ProfRec { cudaEvent_t e0, es, e1, e2; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
 
 static int cap_for_k(int k) {
   if (k <= 224) return 512;
@@ -65,12 +72,33 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   if (smax < 1) smax = 1;
   if (S > smax) S = smax;
   pl->S = (int)S;
+  pl->keep = (int)(8192 / S);
+  if (pl->keep < k) pl->keep = k;
+  if (pl->keep > cap - 32) pl->keep = cap - 32;
+  // threshold seeding (tensor-core path, large corpora): the first seed_rows rows are scored, the
+  // maximum of every 16-row group is kept, and the k-th largest group maximum - a score that at
+  // least k distinct rows reach - becomes the initial shared threshold of each query
+  pl->seed_rows = 0;
+  pl->seed_S = 0;
+  if (tc && n >= 262144 && k <= 256) {
+    int64_t sr = n / 64;
+    if (sr < 8192) sr = 8192;
+    if (sr > 16384) sr = 16384;
+    sr = (sr + pl->tile_n - 1) / pl->tile_n * pl->tile_n;
+    if (sr / 16 >= 4 * (int64_t)k) {
+      pl->seed_rows = (int)sr;
+      int64_t st = sr / pl->tile_n;
+      int64_t ss = (sm_count() + pl->MB - 1) / pl->MB;
+      pl->seed_S = (int)(ss < 1 ? 1 : (ss > st ? st : ss));
+    }
+  }
   size_t items = (size_t)pl->MB * pl->S;
   size_t off = 0;
   pl->off_lists = off;  off = align_up(off + items * pl->rows_per_item * (size_t)cap * 8, 256);
   pl->off_counts = off; off = align_up(off + items * pl->rows_per_item * 4, 256);
   pl->off_gthr = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * 4, 256);
   pl->off_keys = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * k * 8, 256);
+  pl->off_seed = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * (pl->seed_rows / 16) * 4, 256);
   pl->total = off;
   return RAGARC_OK;
 }
@@ -96,14 +124,34 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   int* counts = (int*)(ws + pl.off_counts);
   uint32_t* gthr = (uint32_t*)(ws + pl.off_gthr);
   RA_CUDA(cudaMemsetAsync(counts, 0, (pl.off_keys - pl.off_counts), stream));  // counts + gthr
+  ProfRec pr{};
+  const bool prof = g_prof_on.load() != 0;
+  if (prof) {
+    RA_CUDA(cudaEventCreate(&pr.e0)); RA_CUDA(cudaEventCreate(&pr.e1)); RA_CUDA(cudaEventCreate(&pr.e2));
+    RA_CUDA(cudaEventCreate(&pr.es));
+    RA_CUDA(cudaEventRecord(pr.e0, stream));
+  }
   if (n > 0) {
     if (use == RAGARC_DENSE_TCGEN05)
-      rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, stream);
-    else
+      rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr,
+                           (float*)(ws + pl.off_seed), prof ? pr.es : nullptr, stream);
+    else {
+      if (prof) RA_CUDA(cudaEventRecord(pr.es, stream));
       rc = launch_dense_simt(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, stream);
+    }
     if (rc) return rc;
+  } else if (prof) {
+    RA_CUDA(cudaEventRecord(pr.es, stream));
   }
-  return launch_merge_lists(lists, counts, pl, nq, k, id_base, out_keys, out_scores, out_ids, stream);
+  if (prof) RA_CUDA(cudaEventRecord(pr.e1, stream));
+  rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, out_keys, out_scores, out_ids, stream);
+  if (rc) return rc;
+  if (prof) {
+    RA_CUDA(cudaEventRecord(pr.e2, stream));
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(pr);
+  }
+  return RAGARC_OK;
 }
 
 }  // namespace ragarc
@@ -115,6 +163,32 @@ extern "C" {
 int ragarc_abi_version(void) { return RAGARC_ABI_VERSION; }
 const char* ragarc_last_error(void) { return g_err; }
 uint64_t ragarc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ragarc_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return RAGARC_OK; }
+
+int ragarc_profile_read(double* seed_ms_sum_host, double* score_ms_sum_host, double* merge_ms_sum_host,
+                        int* n_host) {
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  double a = 0, b = 0, c = 0;
+  for (auto& r : recs) {
+    RA_CUDA(cudaEventSynchronize(r.e2));
+    float ms = 0, m0 = 0, m1 = 0;
+    RA_CUDA(cudaEventElapsedTime(&ms, r.e0, r.es));
+    RA_CUDA(cudaEventElapsedTime(&m0, r.es, r.e1));
+    RA_CUDA(cudaEventElapsedTime(&m1, r.e1, r.e2));
+    c += ms; a += m0; b += m1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.es); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2);
+  }
+  if (seed_ms_sum_host) *seed_ms_sum_host = c;
+  if (score_ms_sum_host) *score_ms_sum_host = a;
+  if (merge_ms_sum_host) *merge_ms_sum_host = b;
+  if (n_host) *n_host = (int)recs.size();
+  return RAGARC_OK;
+}
 
 size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k) {
   // worst case over the two paths so that the caller can size once

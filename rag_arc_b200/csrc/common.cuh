@@ -89,6 +89,26 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
   return v;
 }
 
+// Histogram increment used by every radix-select pass.  (A __match_any_sync-aggregated variant was
+// measured slower on B200 than plain shared-memory atomics: merge 84 -> 113 us, see profiles/.)
+__device__ __forceinline__ void hist_add_agg(uint32_t* hist, uint32_t bin, bool valid) {
+  if (valid) atomicAdd(&hist[bin], 1u);
+}
+
+// Radix passes start at the highest bit in which the keys actually differ (given the OR and AND of
+// all keys): the first 8-bit digit then resolves the keys' real range instead of their shared
+// leading bits.  Later digits step down by 8, the last one is clamped to shift 0.
+__device__ __forceinline__ int first_varying_shift(uint64_t all_or, uint64_t all_and) {
+  const uint64_t diff = all_or ^ all_and;
+  if (diff == 0) return 0;
+  const int top = 63 - __clzll((long long)diff);
+  return top >= 7 ? top - 7 : 0;
+}
+__device__ __forceinline__ uint64_t high_bytes_mask(int shift) {   // bits above the digit at `shift`
+  return shift + 8 >= 64 ? 0ull : ~((1ull << (shift + 8)) - 1ull);
+}
+__device__ __forceinline__ int next_shift(int shift) { return shift >= 8 ? shift - 8 : 0; }
+
 // ---- warp-cooperative prune -------------------------------------------------------------------
 // Keeps exactly the k largest keys of list[0..n) (n > k, keys distinct) at list[0..k) and
 // returns ord of the k-th largest score.  MSB-first 8-bit radix select over the 64-bit keys with
@@ -158,6 +178,96 @@ static __device__ __noinline__ uint32_t warp_prune(uint64_t* __restrict__ list, 
   return warp_min_u32(min_ord);
 }
 
+// Register-resident variant for lists of at most 32*R keys: every key is loaded once, up front
+// (R independent loads in flight per lane instead of one L2 round trip per element and pass), the
+// radix passes and the compaction then run out of registers.  Same contract as warp_prune.
+template <int R>
+static __device__ __noinline__ uint32_t warp_prune_reg(uint64_t* __restrict__ list, int n, int k,
+                                                       uint32_t* hist) {
+  const int lane = threadIdx.x & 31;
+  uint64_t key[R];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int i = j * 32 + lane;
+    key[j] = (i < n) ? list[i] : 0ull;       // 0 = empty: never selected (valid keys are > 0)
+  }
+  // skip the radix passes over leading bytes that all keys share
+  uint32_t oh = 0, ol = 0, ah = 0xFFFFFFFFu, al = 0xFFFFFFFFu;
+#pragma unroll
+  for (int j = 0; j < R; ++j)
+    if (key[j] != 0ull) {
+      oh |= uint32_t(key[j] >> 32); ol |= uint32_t(key[j]);
+      ah &= uint32_t(key[j] >> 32); al &= uint32_t(key[j]);
+    }
+  oh = __reduce_or_sync(FULL, oh); ol = __reduce_or_sync(FULL, ol);
+  ah = __reduce_and_sync(FULL, ah); al = __reduce_and_sync(FULL, al);
+  const int shift0 = first_varying_shift((uint64_t(oh) << 32) | ol, (uint64_t(ah) << 32) | al);
+  uint64_t mask = high_bytes_mask(shift0);
+  uint64_t prefix = ((uint64_t(ah) << 32) | al) & mask;
+  uint32_t rem = (uint32_t)k;
+#pragma unroll 1
+  for (int shift = shift0;; shift = next_shift(shift)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      hist_add_agg(hist, (uint32_t)(key[j] >> shift) & 0xFFu, key[j] != 0ull && (key[j] & mask) == prefix);
+    __syncwarp();
+    uint32_t h[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_down_sync(FULL, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    const uint32_t excl = incl - sum;
+    const bool here = (excl < rem) && (incl >= rem);
+    const int src = __ffs(__ballot_sync(FULL, here)) - 1;
+    uint32_t D = 0, above = 0, hD = 0;
+    if (lane == src) {
+      uint32_t acc = excl;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (acc + h[j] >= rem) { D = 8 * lane + j; above = acc; hD = h[j]; break; }
+        acc += h[j];
+      }
+    }
+    D = __shfl_sync(FULL, D, src);
+    above = __shfl_sync(FULL, above, src);
+    hD = __shfl_sync(FULL, hD, src);
+    rem -= above;
+    prefix |= uint64_t(D) << shift;
+    mask |= uint64_t(0xFF) << shift;
+    __syncwarp();
+    if (hD == rem || shift == 0) break;
+  }
+  int base = 0;
+  uint32_t min_ord = 0xFFFFFFFFu;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const bool keep = key[j] != 0ull && ((key[j] & mask) >= prefix);
+    const unsigned b = __ballot_sync(FULL, keep);
+    if (keep) {
+      list[base + __popc(b & ((1u << lane) - 1u))] = key[j];
+      min_ord = min(min_ord, uint32_t(key[j] >> 32));
+    }
+    base += __popc(b);
+  }
+  __syncwarp();
+  return warp_min_u32(min_ord);
+}
+
+static __device__ __forceinline__ uint32_t warp_prune_any(uint64_t* list, int n, int k, int cap,
+                                                          uint32_t* hist) {
+  if (cap <= 512) return warp_prune_reg<16>(list, n, k, hist);
+  if (cap <= 1024) return warp_prune_reg<32>(list, n, k, hist);
+  return warp_prune(list, n, k, hist);
+}
+
 // Per-thread (= per query row) running state of the fused selection.
 struct RowState {
   uint64_t* list;     // this (item,row)'s candidate list, capacity `cap` keys
@@ -168,19 +278,19 @@ struct RowState {
 };
 
 // Called warp-uniformly after a chunk of at most `chunk` appends per lane: prunes every lane's
-// list that could overflow on the next chunk.  gthr_row = &shared_threshold[query] or nullptr.
-__device__ __forceinline__ void prune_if_needed(RowState& st, int k, int cap, int chunk,
-                                                uint32_t* gthr_row, uint32_t* hist, bool force) {
+// list that could overflow on the next chunk (limit = cap - chunk), or - at item end - every list
+// longer than `limit` (the merge kernel's per-list budget).  gthr_row = &shared_threshold[query].
+__device__ __forceinline__ void prune_if_needed(RowState& st, int k, int cap, int limit,
+                                                uint32_t* gthr_row, uint32_t* hist) {
   const int lane = threadIdx.x & 31;
-  bool need = force ? (st.cnt > k) : (st.cnt > cap - chunk);
-  unsigned m = __ballot_sync(FULL, need);
+  unsigned m = __ballot_sync(FULL, st.cnt > limit);
   while (m) {
     int src = __ffs(m) - 1;
     m &= m - 1;
     unsigned long long lp = (unsigned long long)st.list;
     lp = __shfl_sync(FULL, lp, src);
     int n = __shfl_sync(FULL, st.cnt, src);
-    uint32_t kth = warp_prune((uint64_t*)lp, n, k, hist);
+    uint32_t kth = warp_prune_any((uint64_t*)lp, n, k, cap, hist);
     if (lane == src) {
       st.cnt = k;
       st.ord_local = kth;
@@ -201,7 +311,10 @@ struct DensePlan {
   int S;               // corpus slices
   int64_t tiles;       // total corpus tiles
   int cap;             // list capacity (keys)
-  size_t off_lists, off_counts, off_gthr, off_keys, total;
+  int keep;            // a list longer than this is pruned to k at item end (S*keep <= 8192)
+  int seed_rows;       // >0: thresholds are seeded from exact scores of the first seed_rows rows
+  int seed_S;          // corpus slices of the seed pass
+  size_t off_lists, off_counts, off_gthr, off_keys, off_seed, total;
 };
 
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* plan, int* path_out);
@@ -211,7 +324,9 @@ int launch_dense_simt(const void* corpus, int64_t n, int d, int dtype, const voi
                       cudaStream_t stream);
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                     int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
-                    cudaStream_t stream);
+                    float* seed_scores, cudaEvent_t after_seed, cudaStream_t stream);
+int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, uint32_t* gthr,
+                       cudaStream_t stream);
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries);
 
 // merge of per-slice candidate lists -> sorted keys [nq,k] (+ optional decoded outputs)

@@ -19,7 +19,7 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 template <typename T>
 __global__ void __launch_bounds__(simt::THREADS)
 dense_simt_kernel(const T* __restrict__ X, int64_t n, int d, const T* __restrict__ Q, int nq, int k,
-                  int MB, int S, int64_t tiles, int cap, uint64_t* __restrict__ lists,
+                  int MB, int S, int64_t tiles, int cap, int keep, uint64_t* __restrict__ lists,
                   int* __restrict__ counts, uint32_t* __restrict__ gthr) {
   using namespace simt;
   __shared__ __align__(16) float Qs[BK][LD];
@@ -109,13 +109,13 @@ dense_simt_kernel(const T* __restrict__ X, int64_t n, int d, const T* __restrict
               st.list[st.cnt++] = make_key(v, (uint32_t)(r0 + c));
             }
           }
-          prune_if_needed(st, k, cap, 32, grow, hist[warp], false);
+          prune_if_needed(st, k, cap, cap - 32, grow, hist[warp]);
         }
       }
       // Ss is rewritten only after the next tile's k-loop barriers, which warps 0/1 also reach.
     }
     if (warp < 2) {
-      prune_if_needed(st, k, cap, 32, grow, hist[warp], true);
+      prune_if_needed(st, k, cap, keep, grow, hist[warp]);
       counts[(size_t)item * BQ + tid] = st.cnt;
     }
     __syncthreads();
@@ -130,7 +130,7 @@ int launch_dense_simt(const void* corpus, int64_t n, int d, int dtype, const voi
   if (grid < 1) grid = 1;
 #define RA_SIMT_LAUNCH(T)                                                                        \
   dense_simt_kernel<T><<<grid, simt::THREADS, 0, stream>>>((const T*)corpus, n, d, (const T*)queries, \
-      nq, k, pl.MB, pl.S, pl.tiles, pl.cap, lists, counts, gthr)
+      nq, k, pl.MB, pl.S, pl.tiles, pl.cap, pl.keep, lists, counts, gthr)
   if (dtype == RAGARC_F32) RA_SIMT_LAUNCH(float);
   else if (dtype == RAGARC_BF16) RA_SIMT_LAUNCH(__nv_bfloat16);
   else RA_SIMT_LAUNCH(__half);

@@ -24,7 +24,8 @@ constexpr int B_BYTES = BN * BK * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/;
+constexpr int STAGE_F32 = 4 * 32 * 32 * 4;     // per epilogue warp: 32 rows x 32 columns fp32
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/ + STAGE_F32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -89,13 +90,18 @@ struct Params {
   int64_t n;       // corpus rows
   int nq, k, num_kb, MB, S;
   int64_t tiles;
-  int cap;
+  int cap, keep;
   uint32_t idesc;
   uint64_t* lists;
   int* counts;
   uint32_t* gthr;
+  float* seed_out;     // MODE_STORE: [nq, seed_ld] maxima of 16-row groups of rows [0, n)
+  int seed_ld;
 };
 
+constexpr int MODE_TOPK = 0, MODE_STORE = 1;
+
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                 const Params p) {
@@ -108,6 +114,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
   uint32_t* hist = (uint32_t*)(smem + STAGES * STAGE_BYTES + 256);  // [4][256]
+  float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256 + 4 * 256 * 4);  // [4][32][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -186,6 +193,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;          // query row inside the block == TMEM lane
     uint32_t* myhist = hist + (warp - 2) * 256;
+    // per-warp staging of one 32x32 chunk: thread `lane` owns row `lane` (128 B); 16-byte chunks are
+    // XOR-swizzled by (lane & 7) so that the 128-bit stores of a warp spread over all banks
+    float* mystage = stage_all + (warp - 2) * 1024 + lane * 32;
+    const int swz = lane & 7;
     uint32_t tcount = 0;
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
       const int qb = (int)(item % p.MB);
@@ -198,10 +209,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       st.ord_local = 0;
       st.ord_global = 0;
       st.thr = (qrow < p.nq) ? -INFINITY : INFINITY;
-      uint32_t* grow = (qrow < p.nq) ? p.gthr + qrow : nullptr;
+      uint32_t* grow = (MODE == MODE_TOPK && qrow < p.nq) ? p.gthr + qrow : nullptr;
       for (int64_t t = t0; t < t1; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, aphase = (tcount >> 1) & 1;
-        if (grow) {
+        if (MODE == MODE_TOPK && grow) {
           uint32_t g = *(volatile uint32_t*)grow;
           if (g > st.ord_global) { st.ord_global = g; st.thr = combine_thr(st.ord_local, g); }
         }
@@ -216,21 +227,50 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
+          if (MODE == MODE_STORE) {
+            // seed pass: keep only the maximum of every 16 consecutive rows ("group maxima")
+            float g0 = -INFINITY, g1 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float f = __uint_as_float(v[j]);
-            if (f > st.thr) {
-              if (c0 + j < nvalid) st.list[st.cnt++] = make_key(f, (uint32_t)(r0 + c0 + j));
+            for (int j = 0; j < 16; ++j) {
+              g0 = fmaxf(g0, (c0 + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+              g1 = fmaxf(g1, (c0 + 16 + j < nvalid) ? __uint_as_float(v[16 + j]) : -INFINITY);
             }
+            if (qrow < p.nq)
+              *reinterpret_cast<float2*>(p.seed_out + (size_t)qrow * p.seed_ld + ((r0 + c0) >> 4)) = make_float2(g0, g1);
+            continue;
           }
-          prune_if_needed(st, p.k, p.cap, 32, grow, myhist, false);
+          // (1) park the chunk in shared memory so that survivors can be fetched by column index
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<uint4*>(mystage + ((c4 ^ swz) << 2)) =
+                make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+          // (2) branch-free pass mask: bit (31-j) = sign(thr - v[j]) = (v[j] > thr); two chains
+          uint32_t ma = 0, mb = 0;
+          const float thr = st.thr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ma = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j])), ma, 1);
+            mb = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j + 16])), mb, 1);
+          }
+          uint32_t m = (ma << 16) | (mb & 0xFFFFu);
+          if (c0 + 32 > nvalid) m &= ~(0xFFFFFFFFu >> (nvalid - c0));   // drop padding columns
+          // (3) append the survivors in ascending column order
+          while (m) {
+            const int j = __clz(m);
+            m &= ~(0x80000000u >> j);
+            const float f = mystage[(((j >> 2) ^ swz) << 2) | (j & 3)];
+            st.list[st.cnt++] = make_key(f, (uint32_t)(r0 + c0 + j));
+          }
+          prune_if_needed(st, p.k, p.cap, p.cap - 32, grow, myhist);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       }
-      prune_if_needed(st, p.k, p.cap, 32, grow, myhist, true);
-      p.counts[(size_t)item * BM + row] = st.cnt;
+      if (MODE == MODE_TOPK) {
+        prune_if_needed(st, p.k, p.cap, p.keep, grow, myhist);
+        p.counts[(size_t)item * BM + row] = st.cnt;
+      }
     }
   }
 
@@ -279,14 +319,14 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int
 
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries) {
   if (dtype != RAGARC_BF16 && dtype != RAGARC_F16) return false;
-  if (d % 8 != 0 || n <= 0) return false;
+  if (d % 8 != 0 || n <= 0 || n >= (int64_t)0x7FFFFF00ll) return false;
   if (((uintptr_t)corpus & 15) || ((uintptr_t)queries & 15)) return false;
   return true;
 }
 
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                     int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
-                    cudaStream_t stream) {
+                    float* seed_scores, cudaEvent_t after_seed, cudaStream_t stream) {
   using namespace tc;
   RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
              "dense tcgen05: needs bf16/fp16, d %% 8 == 0 and 16-byte aligned base pointers");
@@ -297,19 +337,36 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   if (rc) return rc;
   Params p;
   p.n = n; p.nq = nq; p.k = k; p.num_kb = (d + BK - 1) / BK; p.MB = pl.MB; p.S = pl.S;
-  p.tiles = pl.tiles; p.cap = pl.cap; p.lists = lists; p.counts = counts; p.gthr = gthr;
+  p.tiles = pl.tiles; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
+  p.seed_out = nullptr; p.seed_ld = 0;
   const uint32_t fmt = dtype == RAGARC_BF16 ? 1u : 0u;
   // instruction descriptor (kind::f16): D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major,
   // N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  if (pl.seed_rows > 0) {
+    // seed pass: exact scores of the first seed_rows rows -> k-th largest per query -> gthr
+    Params ps = p;
+    CUtensorMap mxs;
+    rc = make_map(&mxs, corpus, pl.seed_rows, d, dtype, BN);
+    if (rc) return rc;
+    ps.n = pl.seed_rows;
+    ps.tiles = (pl.seed_rows + BN - 1) / BN;
+    ps.S = pl.seed_S;
+    ps.seed_out = seed_scores;
+    ps.seed_ld = pl.seed_rows / 16;
+    int64_t sitems = (int64_t)ps.MB * ps.S;
+    int sgrid = (int)(sitems < sm_count() ? sitems : sm_count());
+    dense_tc_kernel<MODE_STORE><<<sgrid, THREADS, SMEM_BYTES, stream>>>(mq, mxs, ps);
+    RA_LAUNCH_CHECK();
+    rc = launch_seed_select(seed_scores, nq, pl.seed_rows / 16, k, gthr, stream);
+    if (rc) return rc;
   }
+  if (after_seed) RA_CUDA(cudaEventRecord(after_seed, stream));
   int64_t items = (int64_t)pl.MB * pl.S;
   int grid = (int)(items < sm_count() ? items : sm_count());
-  dense_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(mq, mx, p);
+  dense_tc_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, stream>>>(mq, mx, p);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

@@ -1,20 +1,98 @@
 // Final selection: merge the per-slice candidate lists of one query (or the all-gathered
-// per-GPU top-k lists) into one sorted top-k.  One CTA per query; the keys (64-bit, larger =
-// better, unique) are bitonic-sorted in shared memory, so the result is deterministic: score
-// descending, ties by ascending row id, independent of how the corpus was tiled or sharded.
+// per-GPU top-k lists) into one sorted top-k.  One CTA per query: the candidate keys (64-bit,
+// larger = better, unique) are gathered into shared memory with one warp per list, the k best are
+// picked by an MSB-first 8-bit radix select (early exit, typically 3 passes) and only those are
+// bitonic-sorted.  The result is deterministic - score descending, ties by ascending row id -
+// independent of how the corpus was tiled, sliced or sharded.
+// Also here: the threshold seeding select (k-th largest of a dense block of scores per query).
 #include "common.cuh"
 
 namespace ragarc {
+
+constexpr int MERGE_THREADS = 512;
+
+// k-th largest of keys[0..T) (T > k): leaves the winners (exactly k) in win[0..k), unordered.
+// hist: 256 words, sel: 3 words, nwin: 1 word of shared memory.
+__device__ __forceinline__ void block_select_topk(const uint64_t* keys, int T, int k, uint64_t* win,
+                                                  uint32_t* hist, uint32_t* sel, uint32_t* nwin,
+                                                  unsigned long long* orand) {
+  // leading bytes common to all keys need no pass
+  if (threadIdx.x == 0) { orand[0] = 0ull; orand[1] = ~0ull; }
+  __syncthreads();
+  {
+    uint32_t oh = 0, ol = 0, ah = 0xFFFFFFFFu, al = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const uint64_t key = keys[i];
+      oh |= uint32_t(key >> 32); ol |= uint32_t(key); ah &= uint32_t(key >> 32); al &= uint32_t(key);
+    }
+    oh = __reduce_or_sync(FULL, oh); ol = __reduce_or_sync(FULL, ol);
+    ah = __reduce_and_sync(FULL, ah); al = __reduce_and_sync(FULL, al);
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(&orand[0], (unsigned long long)((uint64_t(oh) << 32) | ol));
+      atomicAnd(&orand[1], (unsigned long long)((uint64_t(ah) << 32) | al));
+    }
+  }
+  __syncthreads();
+  const int shift0 = first_varying_shift(orand[0], orand[1]);
+  uint64_t mask = high_bytes_mask(shift0);
+  uint64_t prefix = orand[1] & mask;
+  uint32_t rem = (uint32_t)k;
+  for (int shift = shift0;; shift = next_shift(shift)) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int b = 0; b < T; b += blockDim.x) {
+      const int i = b + threadIdx.x;
+      const uint64_t key = i < T ? keys[i] : 0ull;
+      hist_add_agg(hist, (uint32_t)(key >> shift) & 0xFFu, i < T && (key & mask) == prefix);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      uint32_t h[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_down_sync(FULL, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      const uint32_t excl = incl - sum;
+      if (excl < rem && incl >= rem) {
+        uint32_t a = excl;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (a + h[j] >= rem) { sel[0] = 8 * lane + j; sel[1] = a; sel[2] = h[j]; break; }
+          a += h[j];
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t D = sel[0], above = sel[1], hD = sel[2];
+    rem -= above;
+    prefix |= uint64_t(D) << shift;
+    mask |= uint64_t(0xFF) << shift;
+    __syncthreads();
+    if (hD == rem || shift == 0) break;
+  }
+  if (threadIdx.x == 0) *nwin = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const uint64_t key = keys[i];
+    if ((key & mask) >= prefix) win[atomicAdd(nwin, 1u)] = key;
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P) {
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
       for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-        int lo = 2 * i - (i & (stride - 1));
-        int hi = lo + stride;
-        bool desc = (lo & size) == 0;
-        uint64_t a = s[lo], b = s[hi];
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t a = s[lo], b = s[hi];
         if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
       }
     }
@@ -25,7 +103,7 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P) {
 __device__ __forceinline__ void emit_topk(const uint64_t* s, int q, int k, uint64_t id_base,
                                           uint64_t* out_keys, float* out_scores, int64_t* out_ids) {
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    uint64_t key = s[j];
+    const uint64_t key = s[j];
     if (out_keys) {
       uint64_t gk = 0;
       if (key) gk = (key & 0xFFFFFFFF00000000ull) | uint64_t(0xFFFFFFFFu - (uint32_t)(key_row(key) + id_base));
@@ -36,52 +114,168 @@ __device__ __forceinline__ void emit_topk(const uint64_t* s, int q, int k, uint6
   }
 }
 
-// lists[(slice*MB + qb) * rows + r][cap], counts[(slice*MB + qb) * rows + r]
-__global__ void merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts,
-                                   int MB, int S, int rows, int cap, int k, int P, uint64_t id_base,
-                                   uint64_t* out_keys, float* out_scores, int64_t* out_ids) {
-  extern __shared__ uint64_t skeys[];
+// Shared tail: keys[0..T) gathered in smem -> top-k sorted in win[0..PK) -> outputs.
+__device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, int PK, uint64_t* win,
+                                                 uint32_t* hist, uint32_t* sel, uint32_t* nwin,
+                                                 unsigned long long* orand, int q,
+                                                 uint64_t id_base, uint64_t* out_keys, float* out_scores,
+                                                 int64_t* out_ids) {
+  int have;
+  if (T > k) {
+    block_select_topk(keys, T, k, win, hist, sel, nwin, orand);
+    have = k;
+  } else {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) win[i] = keys[i];
+    have = T;
+  }
+  for (int i = have + threadIdx.x; i < PK; i += blockDim.x) win[i] = 0;
+  __syncthreads();
+  block_bitonic_desc(win, PK);
+  emit_topk(win, q, k, id_base, out_keys, out_scores, out_ids);
+}
+
+// lists[(slice*MB + qb) * rows + r][cap], counts[(slice*MB + qb) * rows + r] (<= keep each)
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S,
+                   int rows, int cap, int k, int PK, int tmax, uint64_t id_base, uint64_t* out_keys,
+                   float* out_scores, int64_t* out_ids) {
+  extern __shared__ uint64_t msm[];
+  uint64_t* keys = msm;              // [tmax]
+  uint64_t* win = msm + tmax;        // [PK]
   __shared__ int offs[1025];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sel[3];
+  __shared__ uint32_t nwin;
+  __shared__ unsigned long long orand[2];
   const int q = blockIdx.x;
   const int qb = q / rows, r = q % rows;
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int s = 0; s < S; ++s) {
-      offs[s] = acc;
-      int c = counts[((size_t)s * MB + qb) * rows + r];
-      acc += c < k ? c : k;       // lists are pruned to <= k at item end
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  if (warp == 0) {
+    // exclusive prefix sum of the S list lengths
+    int carry = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      int c = 0;
+      if (s < S) c = counts[((size_t)s * MB + qb) * rows + r];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (s < S) offs[s] = carry + incl - c;
+      carry += __shfl_sync(FULL, incl, 31);
     }
-    offs[S] = acc;
+    if (lane == 0) offs[S] = carry;
   }
   __syncthreads();
-  const int total = offs[S];
-  for (int s = 0; s < S; ++s) {
-    const size_t li = ((size_t)s * MB + qb) * rows + r;
-    const int c = offs[s + 1] - offs[s];
-    const uint64_t* src = lists + li * (size_t)cap;
-    for (int j = threadIdx.x; j < c; j += blockDim.x) skeys[offs[s] + j] = src[j];
+  int total = offs[S];
+  if (total > tmax) total = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
+  // flattened gather: element e -> (list s, position j) by binary search in the offsets, so that
+  // every thread has several independent loads in flight
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int lo = 0, hi = S - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (offs[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    const size_t li = ((size_t)lo * MB + qb) * rows + r;
+    keys[e] = lists[li * (size_t)cap + (e - offs[lo])];
   }
-  for (int j = total + threadIdx.x; j < P; j += blockDim.x) skeys[j] = 0;
-  block_bitonic_desc(skeys, P);
-  emit_topk(skeys, q, k, id_base, out_keys, out_scores, out_ids);
+  __syncthreads();
+  select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
 }
 
 // keys[g][q][k_in] -> top k_out
-__global__ void merge_keys_kernel(const uint64_t* __restrict__ keys, int G, int nq, int k_in, int k_out,
-                                  int P, float* out_scores, int64_t* out_ids) {
-  extern __shared__ uint64_t skeys[];
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_keys_kernel(const uint64_t* __restrict__ in, int G, int nq, int k_in, int k_out, int PK, int tmax,
+                  float* out_scores, int64_t* out_ids) {
+  extern __shared__ uint64_t msm[];
+  uint64_t* keys = msm;
+  uint64_t* win = msm + tmax;
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sel[3];
+  __shared__ uint32_t nwin;
+  __shared__ unsigned long long orand[2];
+  __shared__ uint32_t nvalid;
   const int q = blockIdx.x;
-  const int total = G * k_in;
-  for (int j = threadIdx.x; j < P; j += blockDim.x) {
-    uint64_t v = 0;
-    if (j < total) {
-      int g = j / k_in, i = j % k_in;
-      v = keys[((size_t)g * nq + q) * k_in + i];
-    }
-    skeys[j] = v;
+  if (threadIdx.x == 0) nvalid = 0;
+  __syncthreads();
+  // compact the non-empty keys (0 = empty slot of a short shard)
+  for (int j = threadIdx.x; j < G * k_in; j += blockDim.x) {
+    const int g = j / k_in, i = j % k_in;
+    const uint64_t v = in[((size_t)g * nq + q) * k_in + i];
+    if (v) keys[atomicAdd(&nvalid, 1u)] = v;
   }
-  block_bitonic_desc(skeys, P);
-  emit_topk(skeys, q, k_out, 0, nullptr, out_scores, out_ids);
+  __syncthreads();
+  select_sort_emit(keys, (int)nvalid, k_out, PK, win, hist, sel, &nwin, orand, q, 0, nullptr, out_scores, out_ids);
+}
+
+// Threshold seeding: vals[q][0..S) (fp32; each the maximum score of a distinct group of corpus
+// rows) -> gthr[q] = orderable(k-th largest).  "At least k rows score at least this" is all the
+// main pass needs to start with a tight filter instead of -inf.
+__global__ void __launch_bounds__(MERGE_THREADS)
+seed_select_kernel(const float* __restrict__ scores, int S, int k, uint32_t* __restrict__ gthr) {
+  extern __shared__ uint32_t ords[];   // [S]
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sel[3];
+  const int q = blockIdx.x;
+  const float* row = scores + (size_t)q * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) ords[i] = f32_to_ord(row[i]);
+  __syncthreads();
+  __shared__ uint32_t orand32[2];
+  if (threadIdx.x == 0) { orand32[0] = 0u; orand32[1] = 0xFFFFFFFFu; }
+  __syncthreads();
+  {
+    uint32_t o_ = 0, a_ = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { o_ |= ords[i]; a_ &= ords[i]; }
+    o_ = __reduce_or_sync(FULL, o_); a_ = __reduce_and_sync(FULL, a_);
+    if ((threadIdx.x & 31) == 0) { atomicOr(&orand32[0], o_); atomicAnd(&orand32[1], a_); }
+  }
+  __syncthreads();
+  const uint32_t diff = orand32[0] ^ orand32[1];
+  const int top = diff ? 31 - __clz((int)diff) : 0;
+  const int shift0 = top >= 7 ? top - 7 : 0;
+  uint32_t mask = shift0 + 8 >= 32 ? 0u : ~((1u << (shift0 + 8)) - 1u);
+  uint32_t prefix = orand32[1] & mask, rem = (uint32_t)k;
+  for (int shift = shift0;; shift = next_shift(shift)) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int b = 0; b < S; b += blockDim.x) {
+      const int i = b + threadIdx.x;
+      const uint32_t o = i < S ? ords[i] : 0u;
+      hist_add_agg(hist, (o >> shift) & 0xFFu, i < S && (o & mask) == prefix);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      uint32_t h[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_down_sync(FULL, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      const uint32_t excl = incl - sum;
+      if (excl < rem && incl >= rem) {
+        uint32_t a = excl;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (a + h[j] >= rem) { sel[0] = 8 * lane + j; sel[1] = a; sel[2] = h[j]; break; }
+          a += h[j];
+        }
+      }
+    }
+    __syncthreads();
+    rem -= sel[1];
+    prefix |= sel[0] << shift;
+    mask |= 0xFFu << shift;
+    __syncthreads();
+    if (shift == 0) break;
+  }
+  if (threadIdx.x == 0) gthr[q] = prefix;    // all varying bytes resolved: exact k-th largest ord
 }
 
 static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
@@ -89,15 +283,23 @@ static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
                        uint64_t id_base, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                        cudaStream_t stream) {
-  int P = next_pow2(pl.S * k > k ? pl.S * k : k);
-  RA_REQUIRE(P <= 8192 && pl.S <= 1024, "merge: S*k=%d too large", pl.S * k);
-  int threads = P / 2 < 1024 ? P / 2 : 1024;
-  if (threads < 32) threads = 32;
-  size_t smem = (size_t)P * 8;
-  if (smem > 48 * 1024)
-    RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  merge_lists_kernel<<<nq, threads, smem, stream>>>(lists, counts, pl.MB, pl.S, pl.rows_per_item, pl.cap,
-                                                   k, P, id_base, out_keys, out_scores, out_ids);
+  const int tmax = pl.S * pl.keep;
+  const int PK = next_pow2(k);
+  RA_REQUIRE(tmax <= 8192 && pl.S <= 1024 && PK <= 2048, "merge: S*keep=%d too large", tmax);
+  const size_t smem = (size_t)(tmax + PK) * 8;
+  RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 2048) * 8));
+  merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, pl.S, pl.rows_per_item,
+                                                         pl.cap, k, PK, tmax, id_base, out_keys, out_scores,
+                                                         out_ids);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, uint32_t* gthr,
+                       cudaStream_t stream) {
+  RA_REQUIRE(seed_rows >= k && seed_rows <= 32768, "seed_select: bad group count %d", seed_rows);
+  RA_CUDA(cudaFuncSetAttribute(seed_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  seed_select_kernel<<<nq, MERGE_THREADS, (size_t)seed_rows * 4, stream>>>(seed_scores, seed_rows, k, gthr);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
@@ -112,15 +314,13 @@ extern "C" int ragarc_merge_topk_keys(const uint64_t* keys, int nlists, int nq, 
   RA_REQUIRE(nlists > 0 && nq >= 0 && k_in > 0 && k_out > 0 && k_out <= nlists * k_in,
              "merge_topk_keys: bad shape G=%d nq=%d k_in=%d k_out=%d", nlists, nq, k_in, k_out);
   if (nq == 0) return RAGARC_OK;
-  int P = next_pow2(nlists * k_in);
-  RA_REQUIRE(P <= 8192, "merge_topk_keys: nlists*k_in=%d exceeds 8192", nlists * k_in);
-  int threads = P / 2 < 1024 ? P / 2 : 1024;
-  if (threads < 32) threads = 32;
-  size_t smem = (size_t)P * 8;
-  if (smem > 48 * 1024)
-    RA_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  merge_keys_kernel<<<nq, threads, smem, (cudaStream_t)stream>>>(keys, nlists, nq, k_in, k_out, P,
-                                                                 out_scores, out_ids);
+  const int tmax = nlists * k_in;
+  const int PK = next_pow2(k_out);
+  RA_REQUIRE(tmax <= 16384 && PK <= 2048, "merge_topk_keys: nlists*k_in=%d exceeds 16384", tmax);
+  const size_t smem = (size_t)(tmax + PK) * 8;
+  RA_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 2048) * 8));
+  merge_keys_kernel<<<nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(keys, nlists, nq, k_in, k_out, PK, tmax,
+                                                                      out_scores, out_ids);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
