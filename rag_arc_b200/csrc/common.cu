@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -59,12 +60,19 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   }
   *path_out = use;
   const bool tc = use == RAGARC_DENSE_TCGEN05;
-  pl->rows_per_item = tc ? 128 : 64;
+  // tcgen05 path: CTA pairs (cta_group::2, 256 query rows per work item) once there are enough
+  // queries to fill both halves; RAGARC_TC_CG=1|2 forces a variant (A/B measurements)
+  int cg = nq > 128 ? 2 : 1;
+  {
+    static const char* env = getenv("RAGARC_TC_CG");
+    if (env && (env[0] == '1' || env[0] == '2')) cg = env[0] - '0';
+  }
+  pl->rows_per_item = tc ? 128 * cg : 64;
   pl->tile_n = tc ? 256 : 64;
   pl->MB = (int)ceil_div(nq > 0 ? nq : 1, pl->rows_per_item);
   pl->tiles = ceil_div(n > 0 ? n : 1, pl->tile_n);
   pl->cap = cap;
-  int64_t target_items = (int64_t)sm_count() * (tc ? 2 : 4);
+  int64_t target_items = tc ? (int64_t)(sm_count() / cg) * 2 : (int64_t)sm_count() * 4;
   int64_t S = (target_items + pl->MB / 2) / pl->MB;
   if (S < 1) S = 1;
   if (S > pl->tiles) S = pl->tiles;
@@ -88,7 +96,7 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
     if (sr / 16 >= 4 * (int64_t)k) {
       pl->seed_rows = (int)sr;
       int64_t st = sr / pl->tile_n;
-      int64_t ss = (sm_count() + pl->MB - 1) / pl->MB;
+      int64_t ss = (sm_count() / cg) / pl->MB;
       pl->seed_S = (int)(ss < 1 ? 1 : (ss > st ? st : ss));
     }
   }

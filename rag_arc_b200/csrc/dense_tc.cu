@@ -3,31 +3,53 @@
 //
 //   scores[q, r] = sum_k Q[q,k] * X[r,k]          bf16/fp16 operands, fp32 accumulate in TMEM
 //
-// Work item = (query block of 128 rows, contiguous slice of corpus tiles); a persistent CTA walks
-// its items.  Per corpus tile (256 rows) and per 64-wide k block, one elected thread issues TMA
-// loads of the Q tile [128x64] and the X tile [256x64] into 128B-swizzled shared memory (4-stage
-// mbarrier ring); one elected thread issues tcgen05.mma (M=128, N=256, K=16, cta_group::1) into
-// one of two 256-column TMEM accumulators; four epilogue warps read the finished accumulator
-// with tcgen05.ld (32 lanes x 32 columns: one thread == one query row), compare every score with
-// the query's running threshold in registers and append the survivors to the (item,row)
-// candidate list; lists are pruned warp-cooperatively (common.cuh).  The nq x n score matrix
-// never leaves the SM.  While the epilogue drains accumulator b, the MMA warp fills b^1.
+// Work item = (query block, contiguous slice of corpus tiles); persistent CTAs (CG=1) or CTA pairs
+// (CG=2, one thread-block cluster of two SMs) walk their items.  Per corpus tile (256 rows) and per
+// 64-wide k block one elected thread per CTA issues TMA loads into 128B-swizzled shared memory
+// (mbarrier ring): its own 128 query rows and - CG=1: all 256 corpus rows / CG=2: its half (128)
+// of them.  One elected thread (of the leader CTA) issues tcgen05.mma
+//   CG=1: M=128 x N=256 x K=16, cta_group::1      CG=2: M=256 x N=256 x K=16, cta_group::2
+// into one of two 256-column TMEM accumulators; with CG=2 the pair shares the corpus tile, which
+// halves its L2->SM traffic, and the smaller per-CTA stage allows a 6-deep ring.
+// Four epilogue warps per CTA read the finished accumulator with tcgen05.ld (32 lanes x 32 columns:
+// one thread == one query row), build a branch-free pass mask against the row's running threshold,
+// and append the survivors to the (item,row) candidate list; lists are pruned warp-cooperatively
+// (common.cuh).  The nq x n score matrix never leaves the SM.  While the epilogue drains
+// accumulator b, the MMA warp fills b^1.
+// MODE_STORE is the threshold-seeding variant: instead of selecting, it writes the maximum of every
+// 16 consecutive corpus rows (see merge.cu: seed_select_kernel).
 #include <cuda.h>
 #include "common.cuh"
 
 namespace ragarc {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = BN * BK * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int BM = 128;            // query rows per CTA (= TMEM lanes)
+constexpr int BN = 256;            // corpus rows per tile (= TMEM columns per accumulator)
+constexpr int BK = 64;             // k elements per stage (= one 128-byte swizzle span)
+constexpr int THREADS = 192;       // warp0 TMA, warp1 MMA/TMEM alloc, warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int STAGE_F32 = 4 * 32 * 32 * 4;     // per epilogue warp: 32 rows x 32 columns fp32
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 256 * 4 /*hist*/ + STAGE_F32;
+constexpr int A_BYTES = BM * BK * 2;                       // 16 KB
+constexpr int MISC_BYTES = 256 /*barriers*/ + 4 * 256 * 4 /*hist*/ + 4 * 32 * 32 * 4 /*chunk staging*/;
+
+template <int CG> struct Cfg {
+  static constexpr int BN_CTA = BN / CG;                   // corpus rows this CTA loads per tile
+  static constexpr int B_BYTES = BN_CTA * BK * 2;          // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB / 32 KB
+  static constexpr int STAGES = CG == 1 ? 4 : 6;           // 192 KB either way
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + MISC_BYTES;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -37,6 +59,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 // Bounded spin: a protocol bug traps (error returned to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -50,22 +80,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
+// TMA tile load.  CG=2: the completion bytes are signalled on the LEADER CTA's barrier (the
+// barrier address with the peer bit cleared, as CUTLASS's SM100_TMA_2SM_LOAD does).
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// MMA completion -> mbarrier.  CG=2: arrive on the barrier of BOTH CTAs of the pair.
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 // K-major operand tile in 128B-swizzled shared memory (rows of 64 bf16 = 128 B, 8-row groups
 // 1024 B apart): start>>4 | LBO(ignored for swizzled K-major)=1 | SBO=1024>>4 | version=1 | SW128.
@@ -101,10 +156,12 @@ struct Params {
 
 constexpr int MODE_TOPK = 0, MODE_STORE = 1;
 
-template <int MODE>
+template <int MODE, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                 const Params p) {
+  using C = Cfg<CG>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles_smem = smem;                                    // STAGES x (A | B)
@@ -113,55 +170,66 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tfull_bar = empty_bar + STAGES;                      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
-  uint32_t* hist = (uint32_t*)(smem + STAGES * STAGE_BYTES + 256);  // [4][256]
-  float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256 + 4 * 256 * 4);  // [4][32][32]
+  uint32_t* hist = (uint32_t*)(smem + STAGES * STAGE_BYTES + 256);                // [4][256]
+  float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256 + 4 * 256 * 4);   // [4][32][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();        // 0 = leader CTA of the pair
+  const int unit = CG == 1 ? blockIdx.x : blockIdx.x >> 1;       // persistent worker id
+  const int nunits = CG == 1 ? gridDim.x : gridDim.x >> 1;
+  constexpr int ROWS_ITEM = BM * CG;                             // query rows per work item
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads(); else cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t items = (int64_t)p.MB * p.S;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
+    // ------------------------------ TMA producer (every CTA) ------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int64_t item = unit; item < items; item += nunits) {
         const int qb = (int)(item % p.MB);
         const int64_t s = item / p.MB;
         const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+        const int q0 = qb * ROWS_ITEM + (int)rank * BM;
         for (int64_t t = t0; t < t1; ++t) {
+          const int x0 = (int)(t * BN) + (int)rank * C::BN_CTA;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a = tiles_smem + stage * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(a, &tmap_q, &full_bar[stage], kb * BK, qb * BM);
-            tma_load_2d(a + A_BYTES, &tmap_x, &full_bar[stage], kb * BK, (int)(t * BN));
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);   // both CTAs' bytes
+            tma_load_2d<CG>(a, &tmap_q, &full_bar[stage], kb * BK, q0);
+            tma_load_2d<CG>(a + A_BYTES, &tmap_x, &full_bar[stage], kb * BK, x0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       uint32_t tcount = 0;
-      for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int64_t item = unit; item < items; item += nunits) {
         const int64_t s = item / p.MB;
         const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
         for (int64_t t = t0; t < t1; ++t, ++tcount) {
@@ -178,33 +246,34 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address
-              tc_mma(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
-                     (uint32_t)((kb | k4) != 0));
+              tc_mma<CG>(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
+                         (uint32_t)((kb | k4) != 0));
             }
-            tc_commit(&empty_bar[stage]);      // frees the smem stage when these MMAs retire
+            tc_commit<CG>(&empty_bar[stage]);   // frees the smem stage (in both CTAs) when the MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&tfull_bar[buf]);          // accumulator complete
+          tc_commit<CG>(&tfull_bar[buf]);       // accumulator complete (signalled in both CTAs)
         }
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ----------------------
+    // ------------------------------ epilogue (warps 2..5, every CTA) ----------
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;          // query row inside the block == TMEM lane
+    const int row = quarter * 32 + lane;          // query row inside the CTA == TMEM lane
     uint32_t* myhist = hist + (warp - 2) * 256;
     // per-warp staging of one 32x32 chunk: thread `lane` owns row `lane` (128 B); 16-byte chunks are
     // XOR-swizzled by (lane & 7) so that the 128-bit stores of a warp spread over all banks
     float* mystage = stage_all + (warp - 2) * 1024 + lane * 32;
     const int swz = lane & 7;
     uint32_t tcount = 0;
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int64_t item = unit; item < items; item += nunits) {
       const int qb = (int)(item % p.MB);
       const int64_t s = item / p.MB;
       const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
-      const int qrow = qb * BM + row;
+      const int irow = (int)rank * BM + row;       // row inside the work item
+      const int qrow = qb * ROWS_ITEM + irow;
       RowState st;
-      st.list = p.lists + ((size_t)item * BM + row) * (size_t)p.cap;
+      st.list = p.lists + ((size_t)item * ROWS_ITEM + irow) * (size_t)p.cap;
       st.cnt = 0;
       st.ord_local = 0;
       st.ord_global = 0;
@@ -265,20 +334,26 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) {
+          // the accumulator is drained: tell the MMA issuer (in the leader CTA)
+          if (rank == 0) mbar_arrive(&tempty_bar[buf]); else mbar_arrive_remote(&tempty_bar[buf], 0);
+        }
       }
       if (MODE == MODE_TOPK) {
         prune_if_needed(st, p.k, p.cap, p.keep, grow, myhist);
-        p.counts[(size_t)item * BM + row] = st.cnt;
+        p.counts[(size_t)item * ROWS_ITEM + irow] = st.cnt;
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads(); else cluster_sync_all();   // pair: nobody leaves while the peer still uses us
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -315,6 +390,30 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int
   return RAGARC_OK;
 }
 
+template <int MODE, int CG>
+static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, cudaStream_t stream) {
+  using C = Cfg<CG>;
+  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int64_t items = (int64_t)p.MB * p.S;
+  const int max_units = sm_count() / CG;
+  const int units = (int)(items < max_units ? items : max_units);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RA_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<MODE, CG>, mq, mx, p));
+  count_launch();
+  return RAGARC_OK;
+}
+
 }  // namespace tc
 
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries) {
@@ -330,10 +429,12 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   using namespace tc;
   RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
              "dense tcgen05: needs bf16/fp16, d %% 8 == 0 and 16-byte aligned base pointers");
+  const int cg = pl.rows_per_item / BM;          // 1 or 2 (chosen by the planner)
+  RA_REQUIRE(cg == 1 || cg == 2, "dense tcgen05: bad plan");
   CUtensorMap mq, mx;
   int rc = make_map(&mq, queries, nq, d, dtype, BM);
   if (rc) return rc;
-  rc = make_map(&mx, corpus, n, d, dtype, BN);
+  rc = make_map(&mx, corpus, n, d, dtype, BN / cg);
   if (rc) return rc;
   Params p;
   p.n = n; p.nq = nq; p.k = k; p.num_kb = (d + BK - 1) / BK; p.MB = pl.MB; p.S = pl.S;
@@ -341,34 +442,26 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   p.seed_out = nullptr; p.seed_ld = 0;
   const uint32_t fmt = dtype == RAGARC_BF16 ? 1u : 0u;
   // instruction descriptor (kind::f16): D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major,
-  // N>>3 at [17,23), M>>4 at [24,29)
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  // N>>3 at [17,23), M>>4 at [24,29); M is 128 per CTA, i.e. 256 for a cta_group::2 pair
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * cg) >> 4) << 24);
   if (pl.seed_rows > 0) {
-    // seed pass: exact scores of the first seed_rows rows -> k-th largest per query -> gthr
+    // seed pass over the first seed_rows rows -> group maxima -> k-th largest per query -> gthr
     Params ps = p;
     CUtensorMap mxs;
-    rc = make_map(&mxs, corpus, pl.seed_rows, d, dtype, BN);
+    rc = make_map(&mxs, corpus, pl.seed_rows, d, dtype, BN / cg);
     if (rc) return rc;
     ps.n = pl.seed_rows;
     ps.tiles = (pl.seed_rows + BN - 1) / BN;
     ps.S = pl.seed_S;
     ps.seed_out = seed_scores;
     ps.seed_ld = pl.seed_rows / 16;
-    int64_t sitems = (int64_t)ps.MB * ps.S;
-    int sgrid = (int)(sitems < sm_count() ? sitems : sm_count());
-    dense_tc_kernel<MODE_STORE><<<sgrid, THREADS, SMEM_BYTES, stream>>>(mq, mxs, ps);
-    RA_LAUNCH_CHECK();
+    rc = cg == 1 ? launch_one<MODE_STORE, 1>(mq, mxs, ps, stream) : launch_one<MODE_STORE, 2>(mq, mxs, ps, stream);
+    if (rc) return rc;
     rc = launch_seed_select(seed_scores, nq, pl.seed_rows / 16, k, gthr, stream);
     if (rc) return rc;
   }
   if (after_seed) RA_CUDA(cudaEventRecord(after_seed, stream));
-  int64_t items = (int64_t)pl.MB * pl.S;
-  int grid = (int)(items < sm_count() ? items : sm_count());
-  dense_tc_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, stream>>>(mq, mx, p);
-  RA_LAUNCH_CHECK();
-  return RAGARC_OK;
+  return cg == 1 ? launch_one<MODE_TOPK, 1>(mq, mx, p, stream) : launch_one<MODE_TOPK, 2>(mq, mx, p, stream);
 }
 
 }  // namespace ragarc
