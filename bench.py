@@ -209,14 +209,13 @@ def run_ours(args):
     q_dev = q32.to(torch.bfloat16).contiguous()
     q_host = q32.cpu().pin_memory()
 
-    keys_all = torch.empty((world, BATCH, TOPK), dtype=torch.int64, device=dev) if world > 1 else None
+    from rag_arc_b200.sharded import ShardedFlatIndex
+    sharded = ShardedFlatIndex(x, lo, n_local) if world > 1 else None
 
     def step_device():
         if world == 1:
             return ops.dense_topk(x, q_dev, TOPK, n_rows=n_local)
-        keys = ops.dense_topk_keys(x, q_dev, TOPK, id_base=lo, n_rows=n_local)
-        dist.all_gather_into_tensor(keys_all.view(-1), keys.view(-1))
-        return ops.merge_topk_keys(keys_all, TOPK)
+        return sharded.search(q_dev, TOPK)
 
     res_scores_host = torch.empty((BATCH, TOPK), dtype=torch.float32).pin_memory()
     res_ids_host = torch.empty((BATCH, TOPK), dtype=torch.int64).pin_memory()
@@ -226,10 +225,7 @@ def run_ours(args):
         if world == 1:
             s, i = store.search_batch(q_host, TOPK)
         else:
-            qd = store.index.prepare_queries(q_host)
-            keys = ops.dense_topk_keys(x, qd, TOPK, id_base=lo, n_rows=n_local)
-            dist.all_gather_into_tensor(keys_all.view(-1), keys.view(-1))
-            s, i = ops.merge_topk_keys(keys_all, TOPK)
+            s, i = sharded.search(store.index.prepare_queries(q_host), TOPK)
         res_scores_host.copy_(s, non_blocking=True)
         res_ids_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()

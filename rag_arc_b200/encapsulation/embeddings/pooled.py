@@ -1,0 +1,110 @@
+"""Embedding plugins whose pool + L2-normalise tail runs on the GPU.
+
+The reference's ``HuggingFaceEmbeddings`` (/root/reference
+core/file_management/embeddings/huggingface.py:85-145) hands tokenisation, the transformer,
+pooling and normalisation to ``sentence_transformers`` and converts the result to Python lists
+(:134).  Here the encoder forward stays a plain callable (out of scope), and the part of that call
+that is arithmetic on the hot path - masked mean / CLS / last-token pooling followed by L2
+normalisation - is the fused ``ragarc_pool_normalize`` kernel.  ``embed_documents_tensor`` keeps
+the result on the device so it can feed ``B200VectorStore.add_embeddings`` / ``search_batch``
+without the ``.tolist()`` round trip; ``embed_documents`` / ``embed_query`` keep the reference's
+list-of-floats contract.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ...core.file_management.embeddings.base import Embeddings
+from ... import ops
+
+
+class B200PooledEmbeddings(Embeddings):
+    """``encoder(texts) -> (hidden [B,T,H] CUDA tensor, attention_mask [B,T])``."""
+
+    def __init__(self, encoder: Callable[[List[str]], Tuple[torch.Tensor, torch.Tensor]],
+                 pooling: str = "mean", normalize_embeddings: bool = True, batch_size: int = 64, **kwargs):
+        super().__init__(**kwargs)
+        if pooling not in ("mean", "cls", "last"):
+            raise ValueError("pooling must be 'mean', 'cls' or 'last'")
+        self.encoder = encoder
+        self.pooling = pooling
+        self.normalize_embeddings = normalize_embeddings
+        self.batch_size = batch_size
+
+    def embed_documents_tensor(self, texts: List[str]) -> torch.Tensor:
+        texts = [t.replace("\n", " ") for t in texts]           # huggingface.py:116
+        outs = []
+        for s in range(0, len(texts), self.batch_size):
+            hidden, mask = self.encoder(texts[s:s + self.batch_size])
+            outs.append(ops.pool_normalize(hidden.contiguous(), mask, self.pooling, self.normalize_embeddings))
+        return torch.cat(outs, dim=0) if outs else torch.empty((0, 0))
+
+    def embed_documents(self, texts: List[str]) -> List[List[float]]:
+        return self.embed_documents_tensor(texts).cpu().tolist()
+
+    def embed_query(self, text: str) -> List[float]:
+        return self.embed_documents([text])[0]
+
+    @classmethod
+    def from_pretrained(cls, model_name: str, pooling: str = "mean", normalize_embeddings: bool = True,
+                        device="cuda", dtype=torch.float16, max_length: int = 512, **kwargs):
+        """Wrap a HuggingFace ``AutoModel`` (weights must be available locally)."""
+        from transformers import AutoModel, AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(model_name)
+        model = AutoModel.from_pretrained(model_name, torch_dtype=dtype).to(device).eval()
+
+        @torch.no_grad()
+        def encoder(texts):
+            enc = tok(texts, padding=True, truncation=True, max_length=max_length, return_tensors="pt").to(device)
+            return model(**enc).last_hidden_state, enc["attention_mask"]
+
+        return cls(encoder, pooling=pooling, normalize_embeddings=normalize_embeddings, **kwargs)
+
+
+class TableEmbeddings(Embeddings):
+    """Pre-computed embeddings looked up by text (used when vectors come from an offline job)."""
+
+    def __init__(self, table, **kwargs):
+        super().__init__(**kwargs)
+        self.table = table
+
+    def embed_documents(self, texts: List[str]) -> List[List[float]]:
+        return [np.asarray(self.table[t], dtype=np.float32).tolist() for t in texts]
+
+    def embed_query(self, text: str) -> List[float]:
+        return np.asarray(self.table[text], dtype=np.float32).tolist()
+
+
+class HashEmbeddings(Embeddings):
+    """Deterministic bag-of-tokens embedding: every token gets a fixed pseudo-random direction
+    (seeded by its CRC32), a text is the sum of its tokens' directions.  No model weights needed;
+    texts that share tokens are close.  For demos, smoke tests and registry examples."""
+
+    def __init__(self, dim: int = 384, seed: int = 0, **kwargs):
+        super().__init__(**kwargs)
+        self.dim, self.seed = dim, seed
+        self._cache = {}
+
+    def _tok(self, tok: str) -> np.ndarray:
+        v = self._cache.get(tok)
+        if v is None:
+            rng = np.random.default_rng((zlib.crc32(tok.encode("utf-8")) << 8) ^ self.seed)
+            v = rng.standard_normal(self.dim).astype(np.float32)
+            self._cache[tok] = v
+        return v
+
+    def _embed(self, text: str) -> np.ndarray:
+        toks = text.split()
+        if not toks:
+            return np.zeros(self.dim, np.float32)
+        return np.sum([self._tok(t) for t in toks], axis=0, dtype=np.float32)
+
+    def embed_documents(self, texts: List[str]) -> List[List[float]]:
+        return [self._embed(t).tolist() for t in texts]
+
+    def embed_query(self, text: str) -> List[float]:
+        return self._embed(text).tolist()

@@ -1,0 +1,80 @@
+"""CPU, world_size 2, gloo: the multi-rank plumbing of ``ShardedFlatIndex`` (shard bounds, global
+ids packed into the keys, one all-gather, merge on every rank).  The two CUDA entry points are
+replaced by oracle-backed stand-ins - the kernels themselves are covered by the GPU tests
+(tests/test_gpu_dense.py::test_keys_and_merge_equal_single_shot)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _ord(f32):
+    u = f32.astype(np.float32).view(np.uint32)
+    return np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint64)
+
+
+def _fake_topk_keys(corpus, queries, k, id_base, n_rows=None, **kw):
+    from oracle import dense as odense
+    X = corpus[:n_rows].float().numpy(); Q = queries.float().numpy()
+    D, I = odense.flat_ip_search(X, Q, k)
+    keys = (_ord(D) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - (I.astype(np.uint64) + np.uint64(id_base)))
+    keys[I < 0] = 0
+    return torch.from_numpy(keys.view(np.int64))
+
+
+def _fake_merge(keys, k_out):
+    G, nq, k = keys.shape
+    flat = keys.numpy().view(np.uint64).transpose(1, 0, 2).reshape(nq, G * k)
+    srt = np.sort(flat, axis=1)[:, ::-1][:, :k_out]            # larger key = better (score, then lower id)
+    ids = (np.uint64(0xFFFFFFFF) - (srt & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    o = (srt >> np.uint64(32)).astype(np.uint32)
+    u = np.where(o & 0x80000000, o & 0x7FFFFFFF, ~o).astype(np.uint32)
+    scores = u.view(np.float32).copy()
+    ids[srt == 0] = -1
+    return torch.from_numpy(scores), torch.from_numpy(ids)
+
+
+def _worker(rank, world, port, n, d, nq, k, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rag_arc_b200 import ops, sharded
+    ops.dense_topk_keys = _fake_topk_keys
+    ops.merge_topk_keys = _fake_merge
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    idx = sharded.ShardedFlatIndex(torch.from_numpy(X[lo:hi]), lo)
+    scores, ids = idx.search(torch.from_numpy(Q), k)
+    from oracle import dense as odense
+    D, I = odense.flat_ip_search(X, Q, k)
+    ok = bool((ids.numpy() == I).all() and np.array_equal(scores.numpy(), D))
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("n,k", [(1001, 10), (7, 5)])
+def test_sharded_search_two_ranks_gloo_equals_single_shot(n, k):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, 16, 5, k, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() == 1
