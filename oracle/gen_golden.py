@@ -127,6 +127,35 @@ def gen_dense(ns):
     return len(out["cases"])
 
 
+def _hybrid_cases(ns, texts, queries, vecs, qvecs, bm):
+    table = {}
+    for t, v in zip(texts, vecs):
+        table.setdefault(t, v)
+    table.update({q: v for q, v in zip(queries, qvecs)})
+    table["test"] = np.zeros(vecs.shape[1], np.float32)
+    store = ns.FaissVectorStore.from_texts(texts, TableEmbeddings(table), ids=[str(i) for i in range(len(texts))])
+    dense_r = ns.VectorStoreRetriever(vectorstore=store)
+
+    class Failing(ns.BaseRetriever):
+        def _get_relevant_documents(self, query, **kw):
+            raise RuntimeError("boom")
+
+    import contextlib
+    import io
+    out = []
+    for name, retrievers in (("bm25+dense", [bm, dense_r]), ("dense+bm25", [dense_r, bm]),
+                             ("bm25+fail+dense", [bm, Failing(), dense_r])):
+        mp = ns.MultiPathRetriever(retrievers, top_k_per_retriever=50)
+        for qi, q in enumerate(queries):
+            for top_k in (10, 50):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    docs = mp.invoke(q, top_k=top_k)
+                out.append({"combo": name, "query": qi, "top_k": top_k,
+                            "contents_idx": [texts.index(d_.content) for d_ in docs],
+                            "ids": [int(d_.id) for d_ in docs]})
+    return out
+
+
 def gen_bm25_hybrid(ns):
     from oracle.ref_loader import make_bm25_retriever
     rng = np.random.default_rng(7)
@@ -149,34 +178,33 @@ def gen_bm25_hybrid(ns):
     vecs = rng.standard_normal((len(texts), d)).astype(np.float32)
     vecs[40] = vecs[12]
     qvecs = rng.standard_normal((len(queries), d)).astype(np.float32)
-    table = {}
-    for t, v in zip(texts, vecs):
-        table.setdefault(t, v)
-    table.update({q: v for q, v in zip(queries, qvecs)})
-    table["test"] = np.zeros(d, np.float32)
-    store = ns.FaissVectorStore.from_texts(texts, TableEmbeddings(table), ids=[str(i) for i in range(len(texts))])
-    dense_r = ns.VectorStoreRetriever(vectorstore=store)
-
-    class Failing(ns.BaseRetriever):
-        def _get_relevant_documents(self, query, **kw):
-            raise RuntimeError("boom")
-
-    import contextlib
-    import io
-    for name, retrievers in (("bm25+dense", [bm, dense_r]), ("dense+bm25", [dense_r, bm]),
-                             ("bm25+fail+dense", [bm, Failing(), dense_r])):
-        mp = ns.MultiPathRetriever(retrievers, top_k_per_retriever=50)
-        for qi, q in enumerate(queries):
-            for top_k in (10, 50):
-                with contextlib.redirect_stdout(io.StringIO()):
-                    docs = mp.invoke(q, top_k=top_k)
-                out["hybrid"].append({"combo": name, "query": qi, "top_k": top_k,
-                                      "contents_idx": [texts.index(d_.content) for d_ in docs],
-                                      "ids": [int(d_.id) for d_ in docs]})
+    out["hybrid"] = _hybrid_cases(ns, texts, queries, vecs, qvecs, bm)
     np.savez_compressed(os.path.join(GOLD, "hybrid_small.npz"), vecs=vecs, qvecs=qvecs)
     with open(os.path.join(GOLD, "bm25_hybrid_small.json"), "w") as f:
         json.dump(out, f)
-    return len(out["bm25"]) + len(out["hybrid"])
+
+    # second set built to be free of BM25 ties inside the top 50 (every document has a distinct
+    # length and contains the frequent words), so the reference's unstable argsort order is
+    # irrelevant and its fused ranking can be compared exactly
+    vocab2 = [f"v{i}" for i in range(25)]
+    p2 = 1.0 / np.arange(1, 26) ** 0.8
+    p2 /= p2.sum()
+    texts2 = [" ".join(rng.choice(vocab2, size=30 + i, p=p2)) for i in range(300)]
+    queries2 = ["v0 v1", "v2", "v0 v3 v5 v0", "v1 v4"]
+    bm2 = make_bm25_retriever(ns, texts2, k=5)
+    vecs2 = rng.standard_normal((len(texts2), d)).astype(np.float32)
+    qvecs2 = rng.standard_normal((len(queries2), d)).astype(np.float32)
+    out2 = {"texts": texts2, "queries": queries2, "bm25": [], "hybrid": _hybrid_cases(ns, texts2, queries2, vecs2, qvecs2, bm2)}
+    for qi, q in enumerate(queries2):
+        sc = np.asarray(bm2.get_scores(q))
+        top = np.sort(sc)[::-1][:52]
+        assert len(np.unique(top)) == len(top), "tie inside the top 52 - regenerate with another seed"
+        out2["bm25"].append({"query": qi, "scores": [float(x) for x in sc]})
+        out2["bm25"].append({"query": qi, "k": 50, "ids": [int(d_.id) for d_ in bm2.invoke(q, k=50)]})
+    np.savez_compressed(os.path.join(GOLD, "hybrid_tiefree.npz"), vecs=vecs2, qvecs=qvecs2)
+    with open(os.path.join(GOLD, "hybrid_tiefree.json"), "w") as f:
+        json.dump(out2, f)
+    return len(out["bm25"]) + len(out["hybrid"]) + len(out2["hybrid"])
 
 
 def main():

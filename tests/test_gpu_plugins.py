@@ -154,15 +154,11 @@ class _Failing(BaseRetriever):
         raise RuntimeError("boom")
 
 
-def _tie_free(scores, k):
-    s = np.sort(scores)[::-1]
-    return len(np.unique(s[:k + 1])) == min(k + 1, len(s))
-
-
-def test_hybrid_retriever_matches_reference_golden_single_and_batch(dev):
-    gold = _bm25_fixture()
+def _hybrid_setup(dev, json_name, npz_name):
+    with open(os.path.join(GOLD, json_name)) as f:
+        gold = json.load(f)
     texts, queries = gold["texts"], gold["queries"]
-    z = np.load(os.path.join(GOLD, "hybrid_small.npz"))
+    z = np.load(os.path.join(GOLD, npz_name))
     table = {}
     for t, v in zip(texts, z["vecs"]):
         table.setdefault(t, v)
@@ -172,17 +168,38 @@ def test_hybrid_retriever_matches_reference_golden_single_and_batch(dev):
     bm = BM25Retriever.from_texts(texts, ids=ids, k=5, device=dev)
     store = B200VectorStore.from_texts(texts, TableEmbeddings(table), ids=ids, device=dev)
     dense = VectorStoreRetriever(vectorstore=store)
-    full = {rec["query"]: np.array(rec["scores"]) for rec in gold["bm25"] if "scores" in rec}
     combos = {"bm25+dense": [bm, dense], "dense+bm25": [dense, bm], "bm25+fail+dense": [bm, _Failing(), dense]}
-    checked = 0
+    return gold, texts, queries, bm, dense, combos
+
+
+def test_hybrid_retriever_equals_reference_multipath_on_tie_free_golden(dev):
+    """tests/golden/hybrid_tiefree.*: the reference's MultiPathRetriever + RRFusion + BM25Retriever +
+    FaissVectorStore run live on a corpus without BM25 ties in the top 50 -> exact equality."""
+    gold, texts, queries, bm, dense, combos = _hybrid_setup(dev, "hybrid_tiefree.json", "hybrid_tiefree.npz")
+    for rec in gold["bm25"]:
+        if "ids" in rec:
+            assert [int(d.id) for d in bm.invoke(queries[rec["query"]], k=50)] == rec["ids"]
+    for rec in gold["hybrid"]:
+        mp = MultiPathRetriever(combos[rec["combo"]], fusion_method=RRFusion(device=dev), top_k_per_retriever=50)
+        with contextlib.redirect_stdout(io.StringIO()):
+            docs = mp.invoke(queries[rec["query"]], top_k=rec["top_k"])
+        assert [int(d.id) for d in docs] == rec["ids"], (rec["combo"], rec["query"], rec["top_k"])
+    mp = MultiPathRetriever([bm, dense], fusion_method=RRFusion(device=dev), top_k_per_retriever=50)
+    batch = mp.invoke_batch(queries, top_k=10)
+    want = [r["ids"] for r in gold["hybrid"] if r["combo"] == "bm25+dense" and r["top_k"] == 10]
+    assert [[int(d.id) for d in b] for b in batch] == want
+
+
+def test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fusion_oracle(dev):
+    """The small golden corpus has duplicate contents and zero-score BM25 tails, where the
+    reference's order depends on numpy's unstable argsort; there the check is against the integer
+    restatement of the reference's fusion fed with OUR per-retriever lists."""
+    gold, texts, queries, bm, dense, combos = _hybrid_setup(dev, "bm25_hybrid_small.json", "hybrid_small.npz")
     for rec in gold["hybrid"]:
         mp = MultiPathRetriever(combos[rec["combo"]], fusion_method=RRFusion(device=dev), top_k_per_retriever=50)
         q = queries[rec["query"]]
         with contextlib.redirect_stdout(io.StringIO()):
             docs = mp.invoke(q, top_k=rec["top_k"])
-        got = [texts.index(d.content) for d in docs]
-        # our own lists -> integer oracle of the reference's fusion: must always agree
-        with contextlib.redirect_stdout(io.StringIO()):
             lists = []
             for r in combos[rec["combo"]]:
                 try:
@@ -190,13 +207,8 @@ def test_hybrid_retriever_matches_reference_golden_single_and_batch(dev):
                 except Exception:
                     lists.append([])
         want_ids, _ = orrf.rrf_fuse_ids(lists, rec["top_k"])
-        assert got == want_ids
-        # the reference's own output: identical whenever its BM25 ranking had no ties in the top 50
-        if _tie_free(full[rec["query"]], 50):
-            assert got == rec["contents_idx"], (rec["combo"], rec["query"], rec["top_k"])
-            checked += 1
-    assert checked >= 6
-    # batched hybrid == per-query hybrid
+        assert [texts.index(d.content) for d in docs] == want_ids
+        assert len(docs) == len(rec["contents_idx"])
     mp = MultiPathRetriever([bm, dense], fusion_method=RRFusion(device=dev), top_k_per_retriever=50)
     batch = mp.invoke_batch(queries, top_k=10)
     single = [mp.invoke(q, top_k=10) for q in queries]
