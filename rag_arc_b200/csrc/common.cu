@@ -72,28 +72,52 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   pl->MB = (int)ceil_div(nq > 0 ? nq : 1, pl->rows_per_item);
   pl->tiles = ceil_div(n > 0 ? n : 1, pl->tile_n);
   pl->cap = cap;
-  int64_t target_items = tc ? (int64_t)(sm_count() / cg) * 2 : (int64_t)sm_count() * 4;
-  int64_t S = (target_items + pl->MB / 2) / pl->MB;
+  // Slice count: work items (MB x S) should fill the persistent workers (SMs, or SM pairs for
+  // cta_group::2) in whole waves - two waves when the merge capacity allows it (the second item of
+  // a worker starts with the thresholds the first wave published), else one.  A ragged last wave
+  // costs a full item time (measured: 163 items on 148 SMs ran 1.3x slower than 148).
+  const int64_t units = tc ? sm_count() / cg : (int64_t)sm_count() * 2;
+  // the merge kernel holds S*keep candidate keys in shared memory: 8192 normally, 16384 when that is
+  // what it takes to give every worker a slice (small batches: the merge grid is tiny then anyway)
+  int64_t merge_cap = 8192;
+  if ((units / pl->MB) * (int64_t)k > merge_cap) merge_cap = 16384;
+  int64_t smax = merge_cap / k;
+  if (smax > 1024) smax = 1024;
+  if (smax > pl->tiles) smax = pl->tiles;
+  if (smax < 1) smax = 1;
+  int64_t S = 0;
+  double best_eff = -1.0;
+  for (int waves = 2; waves >= 1; --waves) {
+    int64_t cand = waves * units / pl->MB;
+    if (cand < 1) cand = 1;
+    if (cand > smax) continue;
+    const int64_t items_c = cand * pl->MB;
+    const double eff = (double)items_c / (double)(ceil_div(items_c, units) * units);
+    if (eff > best_eff + 1e-9) { best_eff = eff; S = cand; }
+  }
+  if (S == 0) S = smax;                 // cannot fill a wave within the merge capacity
+  {
+    static const char* envs = getenv("RAGARC_DENSE_S");     // experiments: force the slice count
+    if (envs && atoi(envs) > 0) S = atoi(envs);
+  }
   if (S < 1) S = 1;
   if (S > pl->tiles) S = pl->tiles;
-  int64_t smax = 8192 / k;            // merge kernel sorts S*k keys in shared memory
-  if (smax < 1) smax = 1;
-  if (S > smax) S = smax;
   pl->S = (int)S;
-  pl->keep = (int)(8192 / S);
+  pl->keep = (int)(merge_cap / S);
   if (pl->keep < k) pl->keep = k;
   if (pl->keep > cap - 32) pl->keep = cap - 32;
-  // threshold seeding (tensor-core path, large corpora): the first seed_rows rows are scored, the
-  // maximum of every 16-row group is kept, and the k-th largest group maximum - a score that at
-  // least k distinct rows reach - becomes the initial shared threshold of each query
+  // threshold seeding (tensor-core path): the first seed_rows rows are scored, the maximum of every
+  // 16-row group is kept, and the k-th largest group maximum - a score that at least k distinct
+  // rows reach - becomes the initial shared threshold of each query.  Needs >= 4k groups for a
+  // tight bound and is only worth it when the seed rows are a small fraction of the corpus.
   pl->seed_rows = 0;
   pl->seed_S = 0;
-  if (tc && n >= 262144 && k <= 256) {
+  if (tc && k <= 256) {
     int64_t sr = n / 64;
-    if (sr < 8192) sr = 8192;
+    if (sr < 64 * (int64_t)k) sr = 64 * (int64_t)k;
     if (sr > 16384) sr = 16384;
     sr = (sr + pl->tile_n - 1) / pl->tile_n * pl->tile_n;
-    if (sr / 16 >= 4 * (int64_t)k) {
+    if (sr / 16 >= 4 * (int64_t)k && n >= 8 * sr) {
       pl->seed_rows = (int)sr;
       int64_t st = sr / pl->tile_n;
       int64_t ss = (sm_count() / cg) / pl->MB;
@@ -106,6 +130,7 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   pl->off_counts = off; off = align_up(off + items * pl->rows_per_item * 4, 256);
   pl->off_gthr = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * 4, 256);
   pl->off_keys = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * k * 8, 256);
+  pl->off_qpad = off;   off = align_up(off + (tc ? (size_t)pl->MB * pl->rows_per_item * d * 2 : 0), 256);
   pl->off_seed = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * (pl->seed_rows / 16) * 4, 256);
   pl->total = off;
   return RAGARC_OK;
@@ -142,7 +167,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   if (n > 0) {
     if (use == RAGARC_DENSE_TCGEN05)
       rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr,
-                           (float*)(ws + pl.off_seed), prof ? pr.es : nullptr, stream);
+                           (float*)(ws + pl.off_seed), ws + pl.off_qpad, prof ? pr.es : nullptr, stream);
     else {
       if (prof) RA_CUDA(cudaEventRecord(pr.es, stream));
       rc = launch_dense_simt(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, stream);

@@ -314,7 +314,7 @@ struct DensePlan {
   int keep;            // a list longer than this is pruned to k at item end (S*keep <= 8192)
   int seed_rows;       // >0: thresholds are seeded from exact scores of the first seed_rows rows
   int seed_S;          // corpus slices of the seed pass
-  size_t off_lists, off_counts, off_gthr, off_keys, off_seed, total;
+  size_t off_lists, off_counts, off_gthr, off_keys, off_qpad, off_seed, total;
 };
 
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* plan, int* path_out);
@@ -324,7 +324,7 @@ int launch_dense_simt(const void* corpus, int64_t n, int d, int dtype, const voi
                       cudaStream_t stream);
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                     int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
-                    float* seed_scores, cudaEvent_t after_seed, cudaStream_t stream);
+                    float* seed_scores, void* qpad, cudaEvent_t after_seed, cudaStream_t stream);
 int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, uint32_t* gthr,
                        cudaStream_t stream);
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries);

@@ -425,14 +425,21 @@ bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const v
 
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                     int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
-                    float* seed_scores, cudaEvent_t after_seed, cudaStream_t stream) {
+                    float* seed_scores, void* qpad, cudaEvent_t after_seed, cudaStream_t stream) {
   using namespace tc;
   RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
              "dense tcgen05: needs bf16/fp16, d %% 8 == 0 and 16-byte aligned base pointers");
   const int cg = pl.rows_per_item / BM;          // 1 or 2 (chosen by the planner)
   RA_REQUIRE(cg == 1 || cg == 2, "dense tcgen05: bad plan");
+  // Queries are staged into a buffer padded with zero rows up to a whole number of work-item rows,
+  // so that every query-tile TMA load is fully in bounds (out-of-bounds fill was measured slower for
+  // tiny batches: 1 query in a 128-row box).
+  const int64_t q_rows = (int64_t)pl.MB * pl.rows_per_item;
+  const size_t q_bytes = (size_t)nq * d * 2;
+  RA_CUDA(cudaMemcpyAsync(qpad, queries, q_bytes, cudaMemcpyDeviceToDevice, stream));
+  if (q_rows > nq) RA_CUDA(cudaMemsetAsync((char*)qpad + q_bytes, 0, (size_t)(q_rows - nq) * d * 2, stream));
   CUtensorMap mq, mx;
-  int rc = make_map(&mq, queries, nq, d, dtype, BM);
+  int rc = make_map(&mq, qpad, q_rows, d, dtype, BM);
   if (rc) return rc;
   rc = make_map(&mx, corpus, n, d, dtype, BN / cg);
   if (rc) return rc;

@@ -84,16 +84,25 @@ __device__ __forceinline__ void block_select_topk(const uint64_t* keys, int T, i
   __syncthreads();
 }
 
+// Bitonic sort (descending) of s[0..P).  Only the first min(blockDim, P/2) threads take part and
+// they synchronise on named barrier 1, so a 128-key sort does not make 512 threads spin through
+// 28 block-wide barriers.  Ends with a block-wide barrier.
 __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P) {
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const uint64_t a = s[lo], b = s[hi];
-        if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+  int nact = P >> 1;
+  if (nact > (int)blockDim.x) nact = blockDim.x;
+  nact = (nact + 31) & ~31;
+  __syncthreads();
+  if ((int)threadIdx.x < nact) {
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < (P >> 1); i += nact) {
+          const int lo = 2 * i - (i & (stride - 1));
+          const int hi = lo + stride;
+          const bool desc = (lo & size) == 0;
+          const uint64_t a = s[lo], b = s[hi];
+          if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
       }
     }
   }
@@ -171,16 +180,21 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   __syncthreads();
   int total = offs[S];
   if (total > tmax) total = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
-  // flattened gather: element e -> (list s, position j) by binary search in the offsets, so that
-  // every thread has several independent loads in flight
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    int lo = 0, hi = S - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (offs[mid] <= e) lo = mid; else hi = mid - 1;
+  // gather: one warp-iteration per (list, 32-key chunk) pair - pure index arithmetic, and the
+  // loads of successive pairs are independent so several are in flight per warp
+  {
+    const int cpl = (tmax / S + 31) >> 5;             // chunks per list (lists hold <= keep = tmax/S keys)
+    const int npairs = S * cpl;
+#pragma unroll 4
+    for (int pr = warp; pr < npairs; pr += nwarp) {
+      const int sl = pr / cpl, ch = pr - sl * cpl;
+      const int o = offs[sl];
+      const int j = (ch << 5) + lane;
+      if (j < offs[sl + 1] - o && o + j < tmax) {
+        const size_t li = ((size_t)sl * MB + qb) * rows + r;
+        keys[o + j] = lists[li * (size_t)cap + j];
+      }
     }
-    const size_t li = ((size_t)lo * MB + qb) * rows + r;
-    keys[e] = lists[li * (size_t)cap + (e - offs[lo])];
   }
   __syncthreads();
   select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
@@ -285,9 +299,9 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan
                        cudaStream_t stream) {
   const int tmax = pl.S * pl.keep;
   const int PK = next_pow2(k);
-  RA_REQUIRE(tmax <= 8192 && pl.S <= 1024 && PK <= 2048, "merge: S*keep=%d too large", tmax);
+  RA_REQUIRE(tmax <= 16384 && pl.S <= 1024 && PK <= 2048, "merge: S*keep=%d too large", tmax);
   const size_t smem = (size_t)(tmax + PK) * 8;
-  RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 2048) * 8));
+  RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 2048) * 8));
   merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, pl.S, pl.rows_per_item,
                                                          pl.cap, k, PK, tmax, id_base, out_keys, out_scores,
                                                          out_ids);

@@ -45,17 +45,36 @@ __global__ void normalize_cast_kernel(const float* __restrict__ src, T* __restri
 }
 
 // ---- pool + normalize: one CTA per sequence ---------------------------------------------------
+// HBM-bound: every kept token row is read once.  The CTA is a (TS token-slices) x (column groups)
+// grid of threads; a thread owns VEC consecutive columns (one 16-byte load per token) and sums the
+// tokens t = slice, slice+TS, ... of its slice with several loads in flight; masked tokens are
+// never read.  Slices are combined through shared memory in a fixed order (deterministic).
+template <typename T> struct PoolVec;
+template <> struct PoolVec<float> { static constexpr int VEC = 4; };
+template <> struct PoolVec<__nv_bfloat16> { static constexpr int VEC = 8; };
+template <> struct PoolVec<__half> { static constexpr int VEC = 8; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&o)[VEC]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) o[i] = load_f32<T>(e + i);
+}
+
 template <typename T>
 __global__ void pool_normalize_kernel(const T* __restrict__ x, const int32_t* __restrict__ mask, int T_len,
-                                      int H, int mode, int normalize, float* __restrict__ out) {
-  extern __shared__ float sred[];     // [blockDim/32]
-  __shared__ float s_cnt;
+                                      int H, int mode, int normalize, int TS, float* __restrict__ out) {
+  constexpr int VEC = PoolVec<T>::VEC;
+  extern __shared__ float psm[];          // [TS][Hpad] partial sums, then [nwarp] norm partials
+  __shared__ float s_cnt, s_norm;
   __shared__ int s_last;
   const int b = blockIdx.x;
   const T* xb = x + (size_t)b * T_len * H;
   const int32_t* mb = mask + (size_t)b * T_len;
+  const int groups = (H + VEC - 1) / VEC;
+  const int Hpad = groups * VEC;
   if (threadIdx.x < 32) {
-    // token count (as float, like the reference's mask.sum) and index of the last kept token
     float c = 0.f; int last = -1;
     for (int t = threadIdx.x; t < T_len; t += 32) if (mb[t] != 0) { c += 1.f; last = t; }
     c = warp_sum(c);
@@ -64,35 +83,66 @@ __global__ void pool_normalize_kernel(const T* __restrict__ x, const int32_t* __
     if (threadIdx.x == 0) { s_cnt = c; s_last = last; }
   }
   __syncthreads();
+  const int g = threadIdx.x % groups, slice = threadIdx.x / groups;
+  const bool vec_ok = (H % VEC == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (slice < TS) {
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const int h0 = g * VEC;
+    if (mode == RAGARC_POOL_MEAN) {
+      for (int t = slice; t < T_len; t += TS) {
+        if (mb[t] == 0) continue;
+        const T* row = xb + (size_t)t * H + h0;
+        if (vec_ok) {
+          float v[VEC];
+          load_vec<T, VEC>(row, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] += v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) if (h0 + i < H) acc[i] += load_f32<T>(row + i);
+        }
+      }
+    } else if (slice == 0) {
+      const int t = mode == RAGARC_POOL_CLS ? 0 : (s_last < 0 ? 0 : s_last);
+      const T* row = xb + (size_t)t * H + h0;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) if (h0 + i < H) acc[i] = load_f32<T>(row + i);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) psm[slice * Hpad + h0 + i] = acc[i];
+  }
+  __syncthreads();
+  // combine slices in order, divide, square-sum
   const float cnt = s_cnt;
   float sq = 0.f;
-  // each thread owns columns h = tid, tid+blockDim, ... ; tokens are summed in order
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float v;
+    float v = 0.f;
     if (mode == RAGARC_POOL_MEAN) {
-      float acc = 0.f;
-      for (int t = 0; t < T_len; ++t)
-        if (mb[t] != 0) acc += load_f32<T>(xb + (size_t)t * H + h);
-      v = __fdiv_rn(acc, fmaxf(cnt, 1e-9f));
-    } else if (mode == RAGARC_POOL_CLS) {
-      v = load_f32<T>(xb + h);
+      for (int sl = 0; sl < TS; ++sl) v += psm[sl * Hpad + h];
+      v = __fdiv_rn(v, fmaxf(cnt, 1e-9f));
     } else {
-      // last token: left-padded batches (mask[T-1]==1) -> T-1, else index of last kept token
-      int t = s_last < 0 ? 0 : s_last;
-      v = load_f32<T>(xb + (size_t)t * H + h);
+      v = psm[h];
     }
     out[(size_t)b * H + h] = v;
     sq = fmaf(v, v, sq);
   }
   if (!normalize) return;
-  sq = warp_sum(sq);
-  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = sq;
   __syncthreads();
-  float tot = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sred[w];
-  const float inv_den = fmaxf(__fsqrt_rn(tot), 1e-12f);
+  sq = warp_sum(sq);
+  float* red = psm;                       // reuse
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    s_norm = fmaxf(__fsqrt_rn(tot), 1e-12f);
+  }
+  __syncthreads();
+  const float den = s_norm;
   for (int h = threadIdx.x; h < H; h += blockDim.x)
-    out[(size_t)b * H + h] = __fdiv_rn(out[(size_t)b * H + h], inv_den);
+    out[(size_t)b * H + h] = __fdiv_rn(out[(size_t)b * H + h], den);
 }
 
 // ---- reciprocal-rank fusion: one CTA per query ------------------------------------------------
@@ -250,13 +300,28 @@ int ragarc_pool_normalize(const void* x, int dtype, const int32_t* mask, int B, 
   RA_REQUIRE(mode >= RAGARC_POOL_MEAN && mode <= RAGARC_POOL_LAST, "pool_normalize: bad mode %d", mode);
   if (B == 0) return RAGARC_OK;
   RA_REQUIRE(x && mask && out, "pool_normalize: null pointer");
-  int threads = H >= 1024 ? 512 : (H >= 256 ? 256 : 128);
-  size_t smem = (threads / 32) * sizeof(float);
+  const int vec = dtype == RAGARC_F32 ? 4 : 8;
+  const int groups = (H + vec - 1) / vec;
+  RA_REQUIRE(groups <= 1024, "pool_normalize: H=%d too large", H);
+  int TS = 1024 / groups;                 // token slices that fit a 1024-thread CTA
+  if (TS > 16) TS = 16;
+  if (TS > T) TS = T;
+  if (TS < 1) TS = 1;
+  int threads = ((groups * TS + 31) / 32) * 32;
+  size_t smem = (size_t)TS * groups * vec * sizeof(float);
+  if (smem < 32 * sizeof(float)) smem = 32 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == RAGARC_F32) pool_normalize_kernel<float><<<B, threads, smem, st>>>((const float*)x, mask, T, H, mode, normalize, out);
-  else if (dtype == RAGARC_BF16) pool_normalize_kernel<__nv_bfloat16><<<B, threads, smem, st>>>((const __nv_bfloat16*)x, mask, T, H, mode, normalize, out);
-  else if (dtype == RAGARC_F16) pool_normalize_kernel<__half><<<B, threads, smem, st>>>((const __half*)x, mask, T, H, mode, normalize, out);
+#define RA_POOL(TT)                                                                                   \
+  do {                                                                                                \
+    if (smem > 48 * 1024)                                                                             \
+      RA_CUDA(cudaFuncSetAttribute(pool_normalize_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    pool_normalize_kernel<TT><<<B, threads, smem, st>>>((const TT*)x, mask, T, H, mode, normalize, TS, out); \
+  } while (0)
+  if (dtype == RAGARC_F32) RA_POOL(float);
+  else if (dtype == RAGARC_BF16) RA_POOL(__nv_bfloat16);
+  else if (dtype == RAGARC_F16) RA_POOL(__half);
   else { set_error("pool_normalize: bad dtype %d", dtype); return RAGARC_ERR_INVALID; }
+#undef RA_POOL
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
