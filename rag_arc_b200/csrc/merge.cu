@@ -144,21 +144,31 @@ __device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, i
 }
 
 // lists[(slice*MB + qb) * rows + r][cap], counts[(slice*MB + qb) * rows + r] (<= keep each)
+//
+// Typical input: S*~160 = ~6000 keys per query of which k=100 are wanted.  Instead of radix-
+// selecting over all of them: (A) the gather also finds the smallest and largest score, (B) one
+// pass histograms the scores into 256 linear bins over that range and locates the bin holding the
+// k-th largest, (C) one compare pass keeps only the keys at or above that bin's lower edge
+// (k + one bin's population, typically ~130) and only those are bitonic-sorted.  Falls back to the
+// full radix select if more than MERGE_WIN keys survive (heavily tied scores).
+constexpr int MERGE_WIN = 512;       // survivors that are sorted directly
+
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S,
                    int rows, int cap, int k, int PK, int tmax, uint64_t id_base, uint64_t* out_keys,
                    float* out_scores, int64_t* out_ids) {
   extern __shared__ uint64_t msm[];
-  uint64_t* keys = msm;              // [tmax]
-  uint64_t* win = msm + tmax;        // [PK]
-  __shared__ int offs[1025];
+  uint64_t* keys = msm;                       // [tmax]
+  uint64_t* win = msm + tmax;                 // [max(PK, MERGE_WIN)] survivors / winners
+  int* offs = (int*)(win + (PK > MERGE_WIN ? PK : MERGE_WIN));   // [S+1]
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sel[3];
-  __shared__ uint32_t nwin;
+  __shared__ uint32_t nwin, omin, omax;
   __shared__ unsigned long long orand[2];
   const int q = blockIdx.x;
   const int qb = q / rows, r = q % rows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  if (threadIdx.x < 256) hist[threadIdx.x] = 0;
   if (warp == 0) {
     // exclusive prefix sum of the S list lengths
     int carry = 0;
@@ -175,29 +185,95 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
       if (s < S) offs[s] = carry + incl - c;
       carry += __shfl_sync(FULL, incl, 31);
     }
-    if (lane == 0) offs[S] = carry;
+    if (lane == 0) { offs[S] = carry; nwin = 0; omin = 0xFFFFFFFFu; omax = 0u; }
   }
   __syncthreads();
   int total = offs[S];
   if (total > tmax) total = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
-  // gather: one warp-iteration per (list, 32-key chunk) pair - pure index arithmetic, and the
-  // loads of successive pairs are independent so several are in flight per warp
+  // (A) gather, one warp per list (round robin), up to 8 independent 32-key chunk loads in flight
   {
-    const int cpl = (tmax / S + 31) >> 5;             // chunks per list (lists hold <= keep = tmax/S keys)
-    const int npairs = S * cpl;
-#pragma unroll 4
-    for (int pr = warp; pr < npairs; pr += nwarp) {
-      const int sl = pr / cpl, ch = pr - sl * cpl;
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
+    for (int sl = warp; sl < S; sl += nwarp) {
       const int o = offs[sl];
-      const int j = (ch << 5) + lane;
-      if (j < offs[sl + 1] - o && o + j < tmax) {
-        const size_t li = ((size_t)sl * MB + qb) * rows + r;
-        keys[o + j] = lists[li * (size_t)cap + j];
+      int c = offs[sl + 1] - o;
+      if (o + c > tmax) c = tmax - o > 0 ? tmax - o : 0;
+      const uint64_t* src = lists + (((size_t)sl * MB + qb) * rows + r) * (size_t)cap;
+      for (int j0 = 0; j0 < c; j0 += 256) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * 32 + lane;
+          v[u] = j < c ? src[j] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * 32 + lane;
+          if (j < c) {
+            keys[o + j] = v[u];
+            const uint32_t hi = uint32_t(v[u] >> 32);
+            lmin = min(lmin, hi); lmax = max(lmax, hi);
+          }
+        }
       }
     }
+    lmin = __reduce_min_sync(FULL, lmin); lmax = __reduce_max_sync(FULL, lmax);
+    if (lane == 0) { atomicMin(&omin, lmin); atomicMax(&omax, lmax); }
   }
   __syncthreads();
-  select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
+  bool fast = total > k;
+  uint32_t bound = 0;
+  if (fast) {
+    // (B) 256 linear bins over [omin, omax]
+    const uint32_t lo = omin, range = omax - omin;
+    const int shift = range >= 256u ? (32 - __clz(range)) - 8 : 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+      atomicAdd(&hist[(uint32_t(keys[i] >> 32) - lo) >> shift], 1u);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t h[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_down_sync(FULL, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      const uint32_t excl = incl - sum;
+      if (excl < (uint32_t)k && incl >= (uint32_t)k) {
+        uint32_t a = excl;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (a + h[j] >= (uint32_t)k) { sel[0] = 8 * lane + j; sel[1] = a + h[j]; break; }
+          a += h[j];
+        }
+      }
+    }
+    __syncthreads();
+    bound = lo + (sel[0] << shift);             // every key with score-ord >= bound survives: sel[1] >= k of them
+    fast = sel[1] <= (uint32_t)MERGE_WIN;
+  }
+  if (fast) {
+    // (C) compact the survivors, sort them, emit the first k
+    for (int b = 0; b < total; b += blockDim.x) {
+      const int i = b + threadIdx.x;
+      const uint64_t key = i < total ? keys[i] : 0ull;
+      const bool keep = i < total && uint32_t(key >> 32) >= bound;
+      const unsigned bal = __ballot_sync(FULL, keep);
+      uint32_t base = 0;
+      if (lane == 0 && bal) base = atomicAdd(&nwin, (uint32_t)__popc(bal));
+      base = __shfl_sync(FULL, base, 0);
+      if (keep) win[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    const int have = (int)nwin;
+    int PW = 32; while (PW < have) PW <<= 1;
+    for (int i = have + threadIdx.x; i < PW; i += blockDim.x) win[i] = 0;
+    block_bitonic_desc(win, PW);
+    emit_topk(win, q, k, id_base, out_keys, out_scores, out_ids);
+  } else {
+    select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
+  }
 }
 
 // keys[g][q][k_in] -> top k_out
@@ -300,8 +376,9 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan
   const int tmax = pl.S * pl.keep;
   const int PK = next_pow2(k);
   RA_REQUIRE(tmax <= 16384 && pl.S <= 1024 && PK <= 2048, "merge: S*keep=%d too large", tmax);
-  const size_t smem = (size_t)(tmax + PK) * 8;
-  RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 2048) * 8));
+  const size_t smem = (size_t)(tmax + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(pl.S + 1) * 4;
+  RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (16384 + 2048) * 8 + 1025 * 4));
   merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, pl.S, pl.rows_per_item,
                                                          pl.cap, k, PK, tmax, id_base, out_keys, out_scores,
                                                          out_ids);
