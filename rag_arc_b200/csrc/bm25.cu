@@ -96,11 +96,63 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
   const int q = q_base + blockIdx.x;
   const int kk = (int64_t)k < n_docs ? k : (int)n_docs;
 
+  __shared__ unsigned long long s_omin, s_omax;
+  bool selected = false;
+  if (threadIdx.x == 0) { s_omin = ~0ull; s_omax = 0ull; nwin = 0; }
+  __syncthreads();
+  if (kk > 0) {
+    // Fast path (3 passes over the accumulator instead of up to 13): linear 256-bin histogram of the
+    // scores over [min, max]; the bin holding the k-th largest score and everything above it
+    // survive, provided that is at most KMAX documents.  Binning is monotone in the score, so all
+    // ties of a survivor survive with it and the final (score, id) sort is exact.
+    uint64_t lmin = ~0ull, lmax = 0ull;
+    for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+      const uint64_t o = f64_to_ord(acc[i]);
+      lmin = o < lmin ? o : lmin; lmax = o > lmax ? o : lmax;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const uint64_t a = __shfl_xor_sync(FULL, lmin, off), b = __shfl_xor_sync(FULL, lmax, off);
+      lmin = a < lmin ? a : lmin; lmax = b > lmax ? b : lmax;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_omin, (unsigned long long)lmin); atomicMax(&s_omax, (unsigned long long)lmax); }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const double mn = ord_to_f64(s_omin), mx = ord_to_f64(s_omax);
+    if (mx > mn && isfinite(mx) && isfinite(mn)) {
+      const double scale = 256.0 / (mx - mn);
+      for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+        int b = (int)((acc[i] - mn) * scale);
+        b = b < 0 ? 0 : (b > 255 ? 255 : b);
+        atomicAdd(&hist[b], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) find_bucket(hist, (uint32_t)kk, sel);
+      __syncthreads();
+      const int bstar = (int)sel[0];
+      if (sel[1] + sel[2] <= (uint32_t)bm25::KMAX) {
+        for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+          const double v = acc[i];
+          int b = (int)((v - mn) * scale);
+          b = b < 0 ? 0 : (b > 255 ? 255 : b);
+          if (b >= bstar) {
+            const uint32_t slot = atomicAdd(&nwin, 1u);
+            win_ord[slot] = f64_to_ord(v); win_id[slot] = (uint32_t)i;
+          }
+        }
+        selected = true;
+      }
+      __syncthreads();
+    }
+  }
+  int have = kk;
+  if (selected) {
+    have = (int)nwin;                  // >= kk survivors; the sort below puts the kk best first
+  } else {
   // composite key = (ord64(score), ~id): 12 digits of 8 bits, MSB first
   uint64_t pre_hi = 0, mask_hi = 0;
   uint32_t pre_lo = 0, mask_lo = 0;
   uint32_t rem = (uint32_t)kk;
-  bool all_bucket = false;
   for (int pass = 0; pass < 12 && kk > 0; ++pass) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -120,9 +172,8 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
     if (pass < 8) { pre_hi |= (uint64_t)D << (56 - 8 * pass); mask_hi |= (uint64_t)0xFF << (56 - 8 * pass); }
     else { pre_lo |= D << (24 - 8 * (pass - 8)); mask_lo |= 0xFFu << (24 - 8 * (pass - 8)); }
     __syncthreads();
-    if (hD == rem) { all_bucket = true; break; }
+    if (hD == rem) break;
   }
-  (void)all_bucket;
   // collect: key >= prefix under the masks  -> exactly kk winners
   if (threadIdx.x == 0) nwin = 0;
   __syncthreads();
@@ -137,9 +188,10 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
     }
   }
   __syncthreads();
+  }
   // sort winners: descending score, ascending id.  P = pow2 >= kk, pad with (0, max id)
-  int P = 1; while (P < kk) P <<= 1;
-  for (int i = kk + threadIdx.x; i < P; i += blockDim.x) { win_ord[i] = 0; win_id[i] = 0xFFFFFFFFu; }
+  int P = 1; while (P < have) P <<= 1;
+  for (int i = have + threadIdx.x; i < P; i += blockDim.x) { win_ord[i] = 0; win_id[i] = 0xFFFFFFFFu; }
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
