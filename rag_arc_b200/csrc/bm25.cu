@@ -3,16 +3,27 @@
 //
 //   score[d] += idf[t] * ( tf * (k1 + 1) / ( tf + k1 * (1 - b + b * dl[d] / avgdl) ) )
 //
-// One CTA owns one query's dense fp64 accumulator (n_docs doubles in the workspace, L2-resident
-// at 100k docs).  Query terms are processed SEQUENTIALLY in query order (duplicates repeat),
-// the postings of one term in parallel: a doc id occurs at most once per posting list, so no
-// two threads touch the same accumulator inside a term and there are no atomics - that, plus
-// the explicit round-to-nearest intrinsics (no FMA contraction), is what makes the fp64 sums
-// reproduce numpy's bit for bit.  HBM/L2-bound gather-scatter: loads of (doc,tf) are coalesced
-// and streamed, the accumulator traffic is random 8-byte read-modify-write.
+// Query terms are processed SEQUENTIALLY in query order (duplicates repeat), the postings of one
+// term in parallel: a doc id occurs at most once per posting list, so no two threads touch the same
+// accumulator inside a term and there are no atomics - that, plus the explicit round-to-nearest
+// intrinsics (no FMA contraction), is what makes the fp64 sums reproduce numpy's bit for bit.
 //
-// Selection: MSB-first radix select over the 96-bit composite key (orderable fp64 score, ~doc id)
-// so that ties resolve to the lowest doc id, then a bitonic sort of the k winners.
+// Two schedules:
+//  * bm25_range_kernel (the top-k path): a CTA owns (query, range of 24 576 consecutive docs) and
+//    keeps that range's fp64 accumulators in SHARED memory (192 KB).  Posting lists are sorted by
+//    doc, so the range's postings of a term are one contiguous span found by binary search; they are
+//    streamed once (coalesced 4-byte loads of doc and tf), the read-modify-write stays on chip, and
+//    the range's top-k is selected straight out of shared memory.  A small merge kernel combines
+//    the per-range candidates.  HBM/L2 traffic per query = its postings (8 B each) + one 8-byte
+//    doc-norm gather per posting - the algorithmic minimum.
+//  * bm25_score_kernel (ragarc_bm25_scores and the fallback for huge k): one CTA per query with a
+//    dense fp64 accumulator row in global memory (L2), followed by bm25_topk_kernel.
+//
+// Selection (block_topk_f64): linear 256-bin histogram over [min,max] -> the bin holding the k-th
+// largest and everything above survive (3 passes); if too many survive (massive ties, e.g. the
+// zero-score tail) an MSB-first radix select over the 96-bit (score, ~doc id) key decides.  Either
+// way ties resolve to the lowest doc id and the winners are bitonic-sorted.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ragarc {
@@ -20,6 +31,8 @@ namespace ragarc {
 namespace bm25 {
 constexpr int THREADS = 1024;
 constexpr int KMAX = 1024;
+constexpr int RANGE = 24576;                      // docs per CTA in the shared-memory schedule
+constexpr int RANGE_SMEM = RANGE * 8;             // 192 KB
 }
 
 __device__ __forceinline__ uint64_t f64_to_ord(double v) {
@@ -31,38 +44,13 @@ __device__ __forceinline__ double ord_to_f64(uint64_t o) {
   uint64_t u = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
   return __longlong_as_double((long long)u);
 }
-
-__global__ void __launch_bounds__(bm25::THREADS)
-bm25_score_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
-                  const int32_t* __restrict__ post_tf, const double* __restrict__ idf,
-                  const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
-                  const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int q_base,
-                  double* __restrict__ acc_all) {
-  const int q = q_base + blockIdx.x;
-  double* acc = acc_all + (size_t)blockIdx.x * n_docs;
-  for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) acc[i] = 0.0;
-  __syncthreads();
-  const int len = q_len[q];
-  for (int t = 0; t < len && t < tmax; ++t) {
-    const int term = q_terms[(size_t)q * tmax + t];
-    if (term >= 0) {
-      const int64_t lo = indptr[term], hi = indptr[term + 1];
-      const double w = idf[term];
-      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const int d = post_doc[i];
-        const double tf = (double)post_tf[i];
-        const double c = __dmul_rn(w, __ddiv_rn(__dmul_rn(tf, k1p1), __dadd_rn(tf, doc_norm[d])));
-        acc[d] = __dadd_rn(acc[d], c);
-      }
-    }
-    __syncthreads();   // orders this term's accumulator updates before the next term's
-  }
+__device__ __forceinline__ double bm25_term(double w, double tf, double k1p1, double norm) {
+  return __dmul_rn(w, __ddiv_rn(__dmul_rn(tf, k1p1), __dadd_rn(tf, norm)));
 }
 
-// block-wide exclusive scan helper over 256 bins held in shared memory: finds the bucket that
-// contains the rem-th largest element.  Returns (digit, count above, count in digit).
+// finds the bucket that contains the rem-th largest element of a 256-bin histogram (warp 0 only;
+// lane owns bins [8*lane, 8*lane+8)): out3 = (digit, count above, count in digit)
 __device__ __forceinline__ void find_bucket(const uint32_t* hist, uint32_t rem, uint32_t* out3) {
-  // executed by warp 0 only; lane owns bins [8*lane, 8*lane+8)
   const int lane = threadIdx.x & 31;
   uint32_t h[8], sum = 0;
 #pragma unroll
@@ -84,29 +72,24 @@ __device__ __forceinline__ void find_bucket(const uint32_t* hist, uint32_t rem, 
   }
 }
 
-__global__ void __launch_bounds__(bm25::THREADS)
-bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int q_base,
-                 double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t sel[3];
-  __shared__ uint64_t win_ord[bm25::KMAX];
-  __shared__ uint32_t win_id[bm25::KMAX];
-  __shared__ uint32_t nwin;
-  const double* acc = acc_all + (size_t)blockIdx.x * n_docs;
-  const int q = q_base + blockIdx.x;
-  const int kk = (int64_t)k < n_docs ? k : (int)n_docs;
+struct TopkScratch {          // shared-memory scratch of block_topk_f64
+  uint32_t hist[256];
+  uint32_t sel[3];
+  uint32_t nwin;
+  unsigned long long omin, omax;
+  uint64_t win_ord[bm25::KMAX];
+  uint32_t win_id[bm25::KMAX];
+};
 
-  __shared__ unsigned long long s_omin, s_omax;
+// Top-kk of acc[0..n) (global or shared memory), ids reported as id_base + index.  On return
+// win_ord/win_id[0..kk) hold the winners sorted by (score desc, id asc).  All threads must call.
+__device__ __forceinline__ void block_topk_f64(const double* acc, int n, int kk, uint32_t id_base, TopkScratch& S) {
   bool selected = false;
-  if (threadIdx.x == 0) { s_omin = ~0ull; s_omax = 0ull; nwin = 0; }
+  if (threadIdx.x == 0) { S.omin = ~0ull; S.omax = 0ull; S.nwin = 0; }
   __syncthreads();
   if (kk > 0) {
-    // Fast path (3 passes over the accumulator instead of up to 13): linear 256-bin histogram of the
-    // scores over [min, max]; the bin holding the k-th largest score and everything above it
-    // survive, provided that is at most KMAX documents.  Binning is monotone in the score, so all
-    // ties of a survivor survive with it and the final (score, id) sort is exact.
     uint64_t lmin = ~0ull, lmax = 0ull;
-    for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const uint64_t o = f64_to_ord(acc[i]);
       lmin = o < lmin ? o : lmin; lmax = o > lmax ? o : lmax;
     }
@@ -115,29 +98,29 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
       const uint64_t a = __shfl_xor_sync(FULL, lmin, off), b = __shfl_xor_sync(FULL, lmax, off);
       lmin = a < lmin ? a : lmin; lmax = b > lmax ? b : lmax;
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&s_omin, (unsigned long long)lmin); atomicMax(&s_omax, (unsigned long long)lmax); }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    if ((threadIdx.x & 31) == 0) { atomicMin(&S.omin, (unsigned long long)lmin); atomicMax(&S.omax, (unsigned long long)lmax); }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) S.hist[i] = 0;
     __syncthreads();
-    const double mn = ord_to_f64(s_omin), mx = ord_to_f64(s_omax);
+    const double mn = ord_to_f64(S.omin), mx = ord_to_f64(S.omax);
     if (mx > mn && isfinite(mx) && isfinite(mn)) {
       const double scale = 256.0 / (mx - mn);
-      for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int b = (int)((acc[i] - mn) * scale);
         b = b < 0 ? 0 : (b > 255 ? 255 : b);
-        atomicAdd(&hist[b], 1u);
+        atomicAdd(&S.hist[b], 1u);
       }
       __syncthreads();
-      if (threadIdx.x < 32) find_bucket(hist, (uint32_t)kk, sel);
+      if (threadIdx.x < 32) find_bucket(S.hist, (uint32_t)kk, S.sel);
       __syncthreads();
-      const int bstar = (int)sel[0];
-      if (sel[1] + sel[2] <= (uint32_t)bm25::KMAX) {
-        for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
+      const int bstar = (int)S.sel[0];
+      if (S.sel[1] + S.sel[2] <= (uint32_t)bm25::KMAX) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
           const double v = acc[i];
           int b = (int)((v - mn) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
           if (b >= bstar) {
-            const uint32_t slot = atomicAdd(&nwin, 1u);
-            win_ord[slot] = f64_to_ord(v); win_id[slot] = (uint32_t)i;
+            const uint32_t slot = atomicAdd(&S.nwin, 1u);
+            S.win_ord[slot] = f64_to_ord(v); S.win_id[slot] = id_base + (uint32_t)i;
           }
         }
         selected = true;
@@ -147,69 +130,196 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
   }
   int have = kk;
   if (selected) {
-    have = (int)nwin;                  // >= kk survivors; the sort below puts the kk best first
+    have = (int)S.nwin;                // >= kk survivors; the sort below puts the kk best first
   } else {
-  // composite key = (ord64(score), ~id): 12 digits of 8 bits, MSB first
-  uint64_t pre_hi = 0, mask_hi = 0;
-  uint32_t pre_lo = 0, mask_lo = 0;
-  uint32_t rem = (uint32_t)kk;
-  for (int pass = 0; pass < 12 && kk > 0; ++pass) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    // composite key = (ord64(score), ~index): 12 digits of 8 bits, MSB first
+    uint64_t pre_hi = 0, mask_hi = 0;
+    uint32_t pre_lo = 0, mask_lo = 0;
+    uint32_t rem = (uint32_t)kk;
+    for (int pass = 0; pass < 12 && kk > 0; ++pass) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) S.hist[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t o = f64_to_ord(acc[i]);
+        const uint32_t nid = ~(uint32_t)i;
+        if ((o & mask_hi) == pre_hi && (nid & mask_lo) == pre_lo) {
+          const uint32_t dig = pass < 8 ? (uint32_t)(o >> (56 - 8 * pass)) & 0xFFu
+                                        : (nid >> (24 - 8 * (pass - 8))) & 0xFFu;
+          atomicAdd(&S.hist[dig], 1u);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) find_bucket(S.hist, rem, S.sel);
+      __syncthreads();
+      const uint32_t D = S.sel[0], above = S.sel[1], hD = S.sel[2];
+      rem -= above;
+      if (pass < 8) { pre_hi |= (uint64_t)D << (56 - 8 * pass); mask_hi |= (uint64_t)0xFF << (56 - 8 * pass); }
+      else { pre_lo |= D << (24 - 8 * (pass - 8)); mask_lo |= 0xFFu << (24 - 8 * (pass - 8)); }
+      __syncthreads();
+      if (hD == rem) break;
+    }
+    if (threadIdx.x == 0) S.nwin = 0;
     __syncthreads();
-    for (int64_t b = 0; b < n_docs; b += blockDim.x) {
-      const int64_t i = b + threadIdx.x;
-      const uint64_t o = i < n_docs ? f64_to_ord(acc[i]) : 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t o = f64_to_ord(acc[i]);
       const uint32_t nid = ~(uint32_t)i;
-      const uint32_t dig = pass < 8 ? (uint32_t)(o >> (56 - 8 * pass)) & 0xFFu
-                                    : (nid >> (24 - 8 * (pass - 8))) & 0xFFu;
-      hist_add_agg(hist, dig, i < n_docs && (o & mask_hi) == pre_hi && (nid & mask_lo) == pre_lo);
+      const uint64_t oh = o & mask_hi;
+      const bool keep = kk > 0 && (oh > pre_hi || (oh == pre_hi && (nid & mask_lo) >= pre_lo));
+      if (keep) {
+        const uint32_t slot = atomicAdd(&S.nwin, 1u);
+        if (slot < bm25::KMAX) { S.win_ord[slot] = o; S.win_id[slot] = id_base + (uint32_t)i; }
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 32) find_bucket(hist, rem, sel);
-    __syncthreads();
-    const uint32_t D = sel[0], above = sel[1], hD = sel[2];
-    rem -= above;
-    if (pass < 8) { pre_hi |= (uint64_t)D << (56 - 8 * pass); mask_hi |= (uint64_t)0xFF << (56 - 8 * pass); }
-    else { pre_lo |= D << (24 - 8 * (pass - 8)); mask_lo |= 0xFFu << (24 - 8 * (pass - 8)); }
-    __syncthreads();
-    if (hD == rem) break;
   }
-  // collect: key >= prefix under the masks  -> exactly kk winners
-  if (threadIdx.x == 0) nwin = 0;
-  __syncthreads();
-  for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) {
-    const uint64_t o = f64_to_ord(acc[i]);
-    const uint32_t nid = ~(uint32_t)i;
-    const uint64_t oh = o & mask_hi;
-    const bool keep = kk > 0 && (oh > pre_hi || (oh == pre_hi && (nid & mask_lo) >= pre_lo));
-    if (keep) {
-      const uint32_t slot = atomicAdd(&nwin, 1u);
-      if (slot < bm25::KMAX) { win_ord[slot] = o; win_id[slot] = (uint32_t)i; }
-    }
-  }
-  __syncthreads();
-  }
-  // sort winners: descending score, ascending id.  P = pow2 >= kk, pad with (0, max id)
+  // sort winners: descending score, ascending id.  P = pow2 >= have, pad with (0, max id)
   int P = 1; while (P < have) P <<= 1;
-  for (int i = have + threadIdx.x; i < P; i += blockDim.x) { win_ord[i] = 0; win_id[i] = 0xFFFFFFFFu; }
+  for (int i = have + threadIdx.x; i < P; i += blockDim.x) { S.win_ord[i] = 0; S.win_id[i] = 0xFFFFFFFFu; }
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
       for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
         const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
         const bool desc = (lo & size) == 0;
-        const uint64_t ao = win_ord[lo], bo = win_ord[hi];
-        const uint32_t ai = win_id[lo], bi = win_id[hi];
+        const uint64_t ao = S.win_ord[lo], bo = S.win_ord[hi];
+        const uint32_t ai = S.win_id[lo], bi = S.win_id[hi];
         const bool a_less = (ao < bo) || (ao == bo && ai > bi);   // "a ranks below b"
-        if (a_less == desc) { win_ord[lo] = bo; win_ord[hi] = ao; win_id[lo] = bi; win_id[hi] = ai; }
+        if (a_less == desc) { S.win_ord[lo] = bo; S.win_ord[hi] = ao; S.win_id[lo] = bi; S.win_id[hi] = ai; }
       }
     }
   }
   __syncthreads();
+}
+
+// ---- dense-accumulator schedule ------------------------------------------------------------------
+__global__ void __launch_bounds__(bm25::THREADS)
+bm25_score_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
+                  const int32_t* __restrict__ post_tf, const double* __restrict__ idf,
+                  const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
+                  const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int q_base,
+                  double* __restrict__ acc_all) {
+  const int q = q_base + blockIdx.x;
+  double* acc = acc_all + (size_t)blockIdx.x * n_docs;
+  for (int64_t i = threadIdx.x; i < n_docs; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const int len = q_len[q];
+  for (int t = 0; t < len && t < tmax; ++t) {
+    const int term = q_terms[(size_t)q * tmax + t];
+    if (term >= 0) {
+      const int64_t lo = indptr[term], hi = indptr[term + 1];
+      const double w = idf[term];
+      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int d = post_doc[i];
+        acc[d] = __dadd_rn(acc[d], bm25_term(w, (double)post_tf[i], k1p1, doc_norm[d]));
+      }
+    }
+    __syncthreads();   // orders this term's accumulator updates before the next term's
+  }
+}
+
+__global__ void __launch_bounds__(bm25::THREADS)
+bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int q_base,
+                 double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ TopkScratch S;
+  const double* acc = acc_all + (size_t)blockIdx.x * n_docs;
+  const int q = q_base + blockIdx.x;
+  const int kk = (int64_t)k < n_docs ? k : (int)n_docs;
+  block_topk_f64(acc, (int)n_docs, kk, 0u, S);
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const bool ok = j < kk;
-    out_scores[(size_t)q * k + j] = ok ? ord_to_f64(win_ord[j]) : -INFINITY;
-    out_ids[(size_t)q * k + j] = ok ? (int64_t)win_id[j] : -1;
+    out_scores[(size_t)q * k + j] = ok ? ord_to_f64(S.win_ord[j]) : -INFINITY;
+    out_ids[(size_t)q * k + j] = ok ? (int64_t)S.win_id[j] : -1;
+  }
+}
+
+// ---- shared-memory range schedule ----------------------------------------------------------------
+// grid = (n_ranges, nq).  cand_ord/cand_id: [nq, n_ranges, k] per-range winners (0 / 0xFFFFFFFF pad).
+__global__ void __launch_bounds__(bm25::THREADS, 1)
+bm25_range_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
+                  const int32_t* __restrict__ post_tf, const double* __restrict__ idf,
+                  const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
+                  const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int k,
+                  uint64_t* __restrict__ cand_ord, uint32_t* __restrict__ cand_id) {
+  extern __shared__ double racc[];                 // [RANGE]
+  __shared__ TopkScratch S;
+  __shared__ int64_t span_lo[32], span_hi[32];
+  __shared__ double span_w[32];
+  const int range = blockIdx.x, n_ranges = gridDim.x, q = blockIdx.y;
+  const int64_t d0 = (int64_t)range * bm25::RANGE;
+  const int nd = (int)((n_docs - d0) < bm25::RANGE ? (n_docs - d0) : bm25::RANGE);
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) racc[i] = 0.0;
+  const int len = q_len[q] < tmax ? q_len[q] : tmax;
+  for (int tb = 0; tb < len; tb += 32) {
+    // the posting span of each of (up to) 32 terms that falls into this doc range
+    if (threadIdx.x < 32) {
+      const int t = tb + threadIdx.x;
+      int64_t a = 0, b = 0; double w = 0.0;
+      if (t < len) {
+        const int term = q_terms[(size_t)q * tmax + t];
+        if (term >= 0) {
+          const int64_t lo = indptr[term], hi = indptr[term + 1];
+          int64_t l = lo, h = hi;                  // lower_bound(d0)
+          while (l < h) { const int64_t m = (l + h) >> 1; if (post_doc[m] < d0) l = m + 1; else h = m; }
+          a = l; h = hi;                           // lower_bound(d0 + nd)
+          while (l < h) { const int64_t m = (l + h) >> 1; if (post_doc[m] < d0 + nd) l = m + 1; else h = m; }
+          b = l; w = idf[term];
+        }
+      }
+      span_lo[threadIdx.x] = a; span_hi[threadIdx.x] = b; span_w[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int nt = len - tb < 32 ? len - tb : 32;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t a = span_lo[t], b = span_hi[t];
+      const double w = span_w[t];
+      for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const int d = post_doc[i];
+        const int l = (int)(d - d0);
+        racc[l] = __dadd_rn(racc[l], bm25_term(w, (double)post_tf[i], k1p1, doc_norm[d]));
+      }
+      __syncthreads();   // term order
+    }
+  }
+  __syncthreads();
+  const int kk = k < nd ? k : nd;
+  block_topk_f64(racc, nd, kk, (uint32_t)d0, S);
+  const size_t base = ((size_t)q * n_ranges + range) * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    cand_ord[base + j] = j < kk ? S.win_ord[j] : 0ull;
+    cand_id[base + j] = j < kk ? S.win_id[j] : 0xFFFFFFFFu;
+  }
+}
+
+// one CTA per query: sort the n_ranges*k candidates by (score desc, id asc), emit the first k
+__global__ void bm25_merge_kernel(const uint64_t* __restrict__ cand_ord, const uint32_t* __restrict__ cand_id,
+                                  int n_ranges, int k, int64_t n_docs, int P, double* __restrict__ out_scores,
+                                  int64_t* __restrict__ out_ids) {
+  extern __shared__ uint64_t mo[];                  // [P] ords then [P] ids (uint32)
+  uint32_t* mi = (uint32_t*)(mo + P);
+  const int q = blockIdx.x, total = n_ranges * k;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    mo[i] = i < total ? cand_ord[(size_t)q * total + i] : 0ull;
+    mi[i] = i < total ? cand_id[(size_t)q * total + i] : 0xFFFFFFFFu;
+  }
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t ao = mo[lo], bo = mo[hi];
+        const uint32_t ai = mi[lo], bi = mi[hi];
+        const bool a_less = (ao < bo) || (ao == bo && ai > bi);
+        if (a_less == desc) { mo[lo] = bo; mo[hi] = ao; mi[lo] = bi; mi[hi] = ai; }
+      }
+    }
+  }
+  __syncthreads();
+  const int kk = (int64_t)k < n_docs ? k : (int)n_docs;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool ok = j < kk && mi[j] != 0xFFFFFFFFu;
+    out_scores[(size_t)q * k + j] = ok ? ord_to_f64(mo[j]) : -INFINITY;
+    out_ids[(size_t)q * k + j] = ok ? (int64_t)mi[j] : -1;
   }
 }
 
@@ -220,15 +330,19 @@ using namespace ragarc;
 extern "C" {
 
 size_t ragarc_bm25_workspace_bytes(int64_t n_docs, int nq) {
-  // one fp64 accumulator row per concurrently scored query; at least one row, at most nq,
-  // capped so that the default workspace stays around 512 MB
+  // dense schedule: one fp64 accumulator row per concurrently scored query, capped near 512 MB;
+  // range schedule: 12 bytes per (query, range, k<=1024) candidate - covered by the same bound
   if (n_docs <= 0 || nq <= 0) return 256;
   size_t row = (size_t)n_docs * 8;
   size_t rows = (size_t)nq;
   size_t cap_rows = (size_t)(512ull << 20) / row;
   if (cap_rows < 1) cap_rows = 1;
   if (rows > cap_rows) rows = cap_rows;
-  return align_up(rows * row, 256);
+  size_t dense = rows * row;
+  size_t n_ranges = (size_t)ceil_div(n_docs, bm25::RANGE);
+  size_t cand = (size_t)nq * n_ranges * bm25::KMAX * 12 + 512;
+  if (cand > (size_t)(1ull << 30)) cand = 0;       // range schedule not used then
+  return align_up(dense > cand ? dense : cand, 256);
 }
 
 static int bm25_check(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
@@ -265,11 +379,33 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
   RA_REQUIRE(k > 0 && k <= bm25::KMAX, "bm25_topk: k=%d must be in [1,%d]", k, bm25::KMAX);
   RA_REQUIRE(out_scores && out_ids, "bm25_topk: null outputs");
   if (nq == 0) return RAGARC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // shared-memory range schedule whenever its candidate buffer fits and the merge is one sort
+  const int64_t n_ranges = ceil_div(n_docs, bm25::RANGE);
+  int P = 32; while (P < n_ranges * k) P <<= 1;
+  const size_t ord_bytes = align_up((size_t)nq * n_ranges * k * 8, 256);
+  const size_t cand_bytes = ord_bytes + (size_t)nq * n_ranges * k * 4;
+  static const bool force_dense = getenv("RAGARC_BM25_DENSE") != nullptr;
+  if (!force_dense && P <= 8192 && n_ranges <= 65535 && nq <= 65535 && workspace && workspace_bytes >= cand_bytes) {
+    uint64_t* cand_ord = (uint64_t*)workspace;
+    uint32_t* cand_id = (uint32_t*)((char*)workspace + ord_bytes);
+    RA_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm25::RANGE_SMEM));
+    bm25_range_kernel<<<dim3((unsigned)n_ranges, (unsigned)nq), bm25::THREADS, bm25::RANGE_SMEM, st>>>(
+        indptr, post_doc, post_tf, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, k, cand_ord, cand_id);
+    RA_LAUNCH_CHECK();
+    const size_t msm = (size_t)P * 12;
+    if (msm > 48 * 1024)
+      RA_CUDA(cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    int mthreads = P / 2 < 1024 ? P / 2 : 1024;
+    if (mthreads < 32) mthreads = 32;
+    bm25_merge_kernel<<<nq, mthreads, msm, st>>>(cand_ord, cand_id, (int)n_ranges, k, n_docs, P, out_scores, out_ids);
+    RA_LAUNCH_CHECK();
+    return RAGARC_OK;
+  }
   const size_t row = (size_t)n_docs * 8;
   RA_REQUIRE(workspace && workspace_bytes >= row, "bm25_topk: workspace %zu < one accumulator row %zu",
              workspace_bytes, row);
   int chunk = (int)(workspace_bytes / row < (size_t)nq ? workspace_bytes / row : (size_t)nq);
-  cudaStream_t st = (cudaStream_t)stream;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int c = nq - q0 < chunk ? nq - q0 : chunk;
     bm25_score_kernel<<<c, bm25::THREADS, 0, st>>>(indptr, post_doc, post_tf, idf, doc_norm, k1_plus_1,
