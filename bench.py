@@ -290,6 +290,7 @@ def run_ours(args):
     qps = args.steps * BATCH / (ms_total * 1e-3)
 
     # ---- timed region: end to end through the plugin with host buffers -----------------------------
+    # (a) synchronous: one search_batch call per step, H2D -> kernels -> D2H back to back
     for _ in range(3):
         step_e2e()
     barrier()
@@ -300,7 +301,30 @@ def run_ours(args):
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    e2e_sync_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    # (b) pipelined public API (1 GPU): the copies of neighbouring steps overlap the kernels; every
+    # step still moves its own queries in and its own results out inside the timed region
+    e2e_ms, e2e_api = e2e_sync_ms, "B200VectorStore.search_batch(pinned host fp32 queries) -> host scores+ids"
+    if world == 1:
+        pipe = store.pipeline(BATCH, TOPK, depth=2)
+        for i in range(4):
+            pipe.result(pipe.submit(q_host))
+        barrier()
+        t0 = time.perf_counter()
+        prev = None
+        for _ in range(args.steps):
+            t = pipe.submit(q_host)
+            if prev is not None:
+                pipe.result(prev)
+            prev = t
+        hs, hi_ = pipe.result(prev)
+        torch.cuda.synchronize()
+        e2e_pipe_ms = (time.perf_counter() - t0) * 1e3
+        assert int(hi_[0, 0]) >= 0
+        if e2e_pipe_ms < e2e_ms:
+            e2e_ms = e2e_pipe_ms
+            e2e_api = ("B200VectorStore.pipeline(nq,k).submit(pinned host fp32 queries)/result() -> pinned host "
+                       "scores+ids; double-buffered, wall-clock timed")
     e2e_qps = args.steps * BATCH / (e2e_ms * 1e-3)
 
     # ---- roofline of the scoring kernel (this rank's launch) ---------------------------------------
@@ -342,10 +366,18 @@ def run_ours(args):
         X32 = x[:n_local].float().cpu().numpy()
         Q32 = q32.cpu().numpy()
         cqps, ndone = cpu_reference_qps(X32, Q32, TOPK, budget_s=12.0)
+        # best case the reference does NOT reach (it has no batch API): one sgemm + top-k for 128 queries
+        Xt = torch.from_numpy(X32); Qt = torch.from_numpy(Q32[:128])
+        tb = time.perf_counter()
+        torch.topk(Qt @ Xt.T, TOPK, dim=1)
+        batched_qps = 128 / (time.perf_counter() - tb)
         cpu = {"value": cqps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{ndone} single-query searches (nq=1, as the reference calls FAISS) over the full "
-                         f"1M x 768 fp32 corpus, numpy sgemv + exact top-k; host cpu_count={os.cpu_count()}"}
-        del X32
+                         f"1M x 768 fp32 corpus, numpy sgemv + exact top-k; host cpu_count={os.cpu_count()}",
+               "batched_sgemm_topk_qps": batched_qps,
+               "batched_note": "128 queries in one torch-CPU sgemm + topk: an upper bound for a batched CPU "
+                               "implementation, not something the reference's API offers"}
+        del X32, Xt
 
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -356,7 +388,7 @@ def run_ours(args):
                    "l2_policy": f"inputs larger than L2 ({n_local * DIM * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIM * 4,
                 "d2h_bytes_per_step": BATCH * TOPK * 12, "ms_per_step": e2e_ms / args.steps,
-                "api": "B200VectorStore.search_batch(pinned host fp32 queries) -> host scores+ids"},
+                "sync_ms_per_step": e2e_sync_ms / args.steps, "api": e2e_api},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

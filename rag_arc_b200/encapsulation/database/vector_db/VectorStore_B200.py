@@ -110,6 +110,70 @@ class FlatIndexB200:
         return D.cpu().numpy(), I.cpu().numpy()
 
 
+class SearchPipeline:
+    """Throughput-oriented batched search over HOST buffers: the host->device copy of batch i+1 and
+    the device->host copy of batch i-1 overlap the kernels of batch i (three CUDA streams, `depth`
+    staging slots, events between them).  Every batch still pays its own H2D and D2H; only their
+    latency is hidden.
+
+        pipe = store.pipeline(nq=1024, k=100)
+        t = pipe.submit(q_host_fp32)          # pinned [nq,d] fp32 tensor (or numpy array)
+        scores, rows = pipe.result(t)         # pinned host tensors, valid until the slot is reused
+    """
+
+    def __init__(self, index: "FlatIndexB200", nq: int, k: int, depth: int = 2):
+        self.index, self.nq, self.k, self.depth = index, nq, k, depth
+        dev = index.device
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "q32": torch.empty((nq, index.d), dtype=torch.float32, device=dev),
+                "q": torch.empty((nq, index.d), dtype=index.dtype, device=dev),
+                "scores": torch.empty((nq, k), dtype=torch.float32, device=dev),
+                "rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
+                "h_scores": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                "h_rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                "copied_in": torch.cuda.Event(), "computed": torch.cuda.Event(), "copied_out": torch.cuda.Event(),
+                "busy": False,
+            })
+        self.n_submitted = 0
+
+    def submit(self, q_host) -> int:
+        ticket = self.n_submitted
+        slot = self.slots[ticket % self.depth]
+        if slot["busy"]:
+            raise RuntimeError("pipeline slot still in use: call result() for older tickets first")
+        qh = torch.as_tensor(q_host)
+        if qh.shape != (self.nq, self.index.d) or qh.dtype != torch.float32:
+            raise ValueError(f"expected float32 [{self.nq},{self.index.d}] queries")
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(slot["computed"])            # previous use of this slot's q32 is done
+            slot["q32"].copy_(qh, non_blocking=True)
+            slot["copied_in"].record(self.s_in)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(slot["copied_in"])
+            self.s_cmp.wait_event(slot["copied_out"])         # previous results of this slot have left
+            ops.normalize_cast(slot["q32"], self.index.dtype, self.index.normalize, out=slot["q"])
+            ops.dense_topk(self.index.rows, slot["q"], self.k, n_rows=self.index.ntotal,
+                           out=(slot["scores"], slot["rows"]))
+            slot["computed"].record(self.s_cmp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["computed"])
+            slot["h_scores"].copy_(slot["scores"], non_blocking=True)
+            slot["h_rows"].copy_(slot["rows"], non_blocking=True)
+            slot["copied_out"].record(self.s_out)
+        slot["busy"] = True
+        self.n_submitted += 1
+        return ticket
+
+    def result(self, ticket: int):
+        slot = self.slots[ticket % self.depth]
+        slot["copied_out"].synchronize()
+        slot["busy"] = False
+        return slot["h_scores"], slot["h_rows"]
+
+
 class B200VectorStore(VectorStore):
     def __init__(self, embedding, index: Optional[FlatIndexB200] = None, index_type: str = "flat",
                  metric: str = "cosine", normalize_L2: bool = False, dtype="float32", device="cuda",
@@ -207,6 +271,12 @@ class B200VectorStore(VectorStore):
         if self.index is None:
             raise ValueError("the store is empty")
         return self.index.search_device(self.index.prepare_queries(queries), k)
+
+    def pipeline(self, nq: int, k: int, depth: int = 2) -> SearchPipeline:
+        """Double-buffered host-in / host-out batched search (see ``SearchPipeline``)."""
+        if self.index is None:
+            raise ValueError("the store is empty")
+        return SearchPipeline(self.index, nq, min(k, max(self.ntotal, 1)), depth)
 
     def similarity_search_batch(self, queries: List[str], k: int = 4) -> List[List[Tuple[Document, float]]]:
         if self.ntotal == 0:

@@ -94,6 +94,26 @@ def test_vector_store_bookkeeping_delete_persist_batch(dev, tmp_path):
     assert got[0].id == "d150"
 
 
+def test_search_pipeline_equals_synchronous_search(dev):
+    rng = np.random.default_rng(11)
+    vecs = rng.standard_normal((5000, 64)).astype(np.float32)
+    store = B200VectorStore.from_embeddings([f"t{i}" for i in range(5000)], vecs, dtype="bfloat16", device=dev)
+    pipe = store.pipeline(nq=32, k=7, depth=2)
+    batches = [torch.from_numpy(rng.standard_normal((32, 64)).astype(np.float32)).pin_memory() for _ in range(5)]
+    got, prev = [], None
+    for b in batches:
+        t = pipe.submit(b)
+        if prev is not None:
+            s, r = pipe.result(prev); got.append((s.clone(), r.clone()))
+        prev = t
+    s, r = pipe.result(prev); got.append((s.clone(), r.clone()))
+    for b, (s, r) in zip(batches, got):
+        ws, wr = store.search_batch(b, 7)
+        assert torch.equal(r, wr.cpu()) and torch.equal(s, ws.cpu())
+    with pytest.raises(ValueError):
+        pipe.submit(torch.zeros((3, 64)))
+
+
 def _bm25_fixture():
     with open(os.path.join(GOLD, "bm25_hybrid_small.json")) as f:
         return json.load(f)
