@@ -156,7 +156,11 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   uint64_t* lists = (uint64_t*)(ws + pl.off_lists);
   int* counts = (int*)(ws + pl.off_counts);
   uint32_t* gthr = (uint32_t*)(ws + pl.off_gthr);
-  RA_CUDA(cudaMemsetAsync(counts, 0, (pl.off_keys - pl.off_counts), stream));  // counts + gthr
+  // list lengths are written for every (item,row) by the scoring kernels, so only the shared
+  // thresholds need a reset - and not even those when the seed pass overwrites all of them
+  if (!(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0 && n > 0))
+    RA_CUDA(cudaMemsetAsync(gthr, 0, (size_t)nq * 4, stream));
+  if (n == 0) RA_CUDA(cudaMemsetAsync(counts, 0, pl.off_gthr - pl.off_counts, stream));
   ProfRec pr{};
   const bool prof = g_prof_on.load() != 0;
   if (prof) {

@@ -19,6 +19,7 @@
 // MODE_STORE is the threshold-seeding variant: instead of selecting, it writes the maximum of every
 // 16 consecutive corpus rows (see merge.cu: seed_select_kernel).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ragarc {
@@ -94,6 +95,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
   }
 }
+// TMA prefetch of a tile into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // MMA completion -> mbarrier.  CG=2: arrive on the barrier of BOTH CTAs of the pair.
@@ -150,6 +155,7 @@ struct Params {
   uint64_t* lists;
   int* counts;
   uint32_t* gthr;
+  int prefetch;        // RAGARC_TC_PREFETCH: L2 prefetch distance in tiles (0 = off; measured 2 % slower when on)
   float* seed_out;     // MODE_STORE: [nq, seed_ld] maxima of 16-row groups of rows [0, n)
   int seed_ld;
 };
@@ -213,7 +219,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int q0 = qb * ROWS_ITEM + (int)rank * BM;
         for (int64_t t = t0; t < t1; ++t) {
           const int x0 = (int)(t * BN) + (int)rank * C::BN_CTA;
+          // corpus rows one tile ahead are pulled into L2 now, so that the ring's refills (which
+          // have ~5 stage-times to land) see L2 latency instead of HBM latency
+          const bool pf = p.prefetch > 0 && (t + p.prefetch < t1);
           for (int kb = 0; kb < p.num_kb; ++kb) {
+            if (pf) tma_prefetch_l2_2d(&tmap_x, kb * BK, x0 + p.prefetch * BN);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a = tiles_smem + stage * STAGE_BYTES;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);   // both CTAs' bytes
@@ -435,11 +445,15 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   // so that every query-tile TMA load is fully in bounds (out-of-bounds fill was measured slower for
   // tiny batches: 1 query in a 128-row box).
   const int64_t q_rows = (int64_t)pl.MB * pl.rows_per_item;
-  const size_t q_bytes = (size_t)nq * d * 2;
-  RA_CUDA(cudaMemcpyAsync(qpad, queries, q_bytes, cudaMemcpyDeviceToDevice, stream));
-  if (q_rows > nq) RA_CUDA(cudaMemsetAsync((char*)qpad + q_bytes, 0, (size_t)(q_rows - nq) * d * 2, stream));
+  const void* qsrc = queries;
+  if (q_rows > nq) {
+    const size_t q_bytes = (size_t)nq * d * 2;
+    RA_CUDA(cudaMemcpyAsync(qpad, queries, q_bytes, cudaMemcpyDeviceToDevice, stream));
+    RA_CUDA(cudaMemsetAsync((char*)qpad + q_bytes, 0, (size_t)(q_rows - nq) * d * 2, stream));
+    qsrc = qpad;
+  }
   CUtensorMap mq, mx;
-  int rc = make_map(&mq, qpad, q_rows, d, dtype, BM);
+  int rc = make_map(&mq, qsrc, q_rows, d, dtype, BM);
   if (rc) return rc;
   rc = make_map(&mx, corpus, n, d, dtype, BN / cg);
   if (rc) return rc;
@@ -447,6 +461,10 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   p.n = n; p.nq = nq; p.k = k; p.num_kb = (d + BK - 1) / BK; p.MB = pl.MB; p.S = pl.S;
   p.tiles = pl.tiles; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
   p.seed_out = nullptr; p.seed_ld = 0;
+  {
+    static const char* env = getenv("RAGARC_TC_PREFETCH");
+    p.prefetch = env ? atoi(env) : 0;
+  }
   const uint32_t fmt = dtype == RAGARC_BF16 ? 1u : 0u;
   // instruction descriptor (kind::f16): D=f32 [4,6), A fmt [7,10), B fmt [10,13), A/B K-major,
   // N>>3 at [17,23), M>>4 at [24,29); M is 128 per CTA, i.e. 256 for a cta_group::2 pair
