@@ -384,7 +384,8 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if DTYPE == "bfloat16" else "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": N_ROWS, "dim": DIM, "batch": BATCH, "k": TOPK,
-                   "rows_per_gpu": n_local, "parallelism": f"row-shard x{world} + NCCL all-gather merge" if world > 1 else "single GPU",
+                   "rows_per_gpu": n_local, "parallelism": (f"row-shard x{world}, key exchange: {sharded.exchange_used}, merge on every rank"
+                                   if world > 1 else "single GPU"),
                    "l2_policy": f"inputs larger than L2 ({n_local * DIM * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIM * 4,
                 "d2h_bytes_per_step": BATCH * TOPK * 12, "ms_per_step": e2e_ms / args.steps,

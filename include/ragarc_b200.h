@@ -99,6 +99,13 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
 int ragarc_merge_topk_keys(const uint64_t* keys, int nlists, int nq, int k_in, int k_out,
                            float* out_scores, int64_t* out_ids, void* stream);
 
+/* Same merge without the all-gather: key_ptrs is a DEVICE array of nlists pointers, entry g
+ * pointing at shard g's [nq, k_in] key block - which may live in a PEER GPU's memory mapped into
+ * this process (NVLink loads inside the merge kernel; rag_arc_b200/sharded.py sets the table up
+ * from symmetric memory handles and orders the accesses with a device-side barrier). */
+int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int nlists, int nq, int k_in,
+                               int k_out, float* out_scores, int64_t* out_ids, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * BM25 (Okapi) scoring over CSR postings.   Replaces rank_bm25.BM25Okapi.get_scores at
  *   core/retrieval/bm25.py:306,332 and np.argsort(scores)[::-1][:k] at :309,:359.

@@ -276,29 +276,45 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   }
 }
 
-// keys[g][q][k_in] -> top k_out
-__global__ void __launch_bounds__(MERGE_THREADS)
-merge_keys_kernel(const uint64_t* __restrict__ in, int G, int nq, int k_in, int k_out, int PK, int tmax,
-                  float* out_scores, int64_t* out_ids) {
-  extern __shared__ uint64_t msm[];
-  uint64_t* keys = msm;
-  uint64_t* win = msm + tmax;
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t sel[3];
-  __shared__ uint32_t nwin;
-  __shared__ unsigned long long orand[2];
-  __shared__ uint32_t nvalid;
-  const int q = blockIdx.x;
-  if (threadIdx.x == 0) nvalid = 0;
-  __syncthreads();
-  // compact the non-empty keys (0 = empty slot of a short shard)
-  for (int j = threadIdx.x; j < G * k_in; j += blockDim.x) {
-    const int g = j / k_in, i = j % k_in;
-    const uint64_t v = in[((size_t)g * nq + q) * k_in + i];
-    if (v) keys[atomicAdd(&nvalid, 1u)] = v;
+// G per-shard result lists per query, each sorted descending (the output format of
+// ragarc_dense_topk_keys; 0 = empty slot, at the tail) -> global top k_out.  No sort: every key's
+// global rank = its position in its own list + the number of larger keys in each other list
+// (binary search in shared memory); keys are unique, so ranks are a permutation.
+// list g of query q lives at (ptrs ? ptrs[g] : base + g*stride_g) + q*k_in  - with `ptrs` the lists
+// may be PEER-GPU memory (NVLink loads), which is how the multi-GPU merge avoids an all-gather.
+__global__ void __launch_bounds__(256)
+merge_sorted_keys_kernel(const uint64_t* __restrict__ base, size_t stride_g, const uint64_t* const* __restrict__ ptrs,
+                         int G, int nq, int k_in, int k_out, float* __restrict__ out_scores,
+                         int64_t* __restrict__ out_ids) {
+  extern __shared__ uint64_t sk[];            // [G][k_in]
+  const int q = blockIdx.x, total = G * k_in;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int g = e / k_in, i = e - g * k_in;
+    const uint64_t* src = (ptrs ? ptrs[g] : base + (size_t)g * stride_g) + (size_t)q * k_in;
+    sk[e] = src[i];
+  }
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    out_scores[(size_t)q * k_out + j] = -INFINITY;
+    out_ids[(size_t)q * k_out + j] = -1;
   }
   __syncthreads();
-  select_sort_emit(keys, (int)nvalid, k_out, PK, win, hist, sel, &nwin, orand, q, 0, nullptr, out_scores, out_ids);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const uint64_t key = sk[e];
+    if (!key) continue;
+    const int g = e / k_in, i = e - g * k_in;
+    int rank = i;
+    for (int h = 0; h < G; ++h) {
+      if (h == g) continue;
+      const uint64_t* lst = sk + h * k_in;
+      int lo = 0, hi = k_in;                  // first index whose key is < `key` (descending list)
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (lst[m] > key) lo = m + 1; else hi = m; }
+      rank += lo;
+    }
+    if (rank < k_out) {
+      out_scores[(size_t)q * k_out + rank] = key_score(key);
+      out_ids[(size_t)q * k_out + rank] = (int64_t)key_row(key);
+    }
+  }
 }
 
 // Threshold seeding: vals[q][0..S) (fp32; each the maximum score of a distinct group of corpus
@@ -399,19 +415,30 @@ int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, u
 
 using namespace ragarc;
 
-extern "C" int ragarc_merge_topk_keys(const uint64_t* keys, int nlists, int nq, int k_in, int k_out,
-                                      float* out_scores, int64_t* out_ids, void* stream) {
-  RA_REQUIRE(keys && out_scores && out_ids, "merge_topk_keys: null pointer");
+static int merge_sorted_launch(const uint64_t* base, size_t stride_g, const uint64_t* const* ptrs, int nlists,
+                               int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream) {
+  RA_REQUIRE(out_scores && out_ids, "merge_topk_keys: null pointer");
   RA_REQUIRE(nlists > 0 && nq >= 0 && k_in > 0 && k_out > 0 && k_out <= nlists * k_in,
              "merge_topk_keys: bad shape G=%d nq=%d k_in=%d k_out=%d", nlists, nq, k_in, k_out);
   if (nq == 0) return RAGARC_OK;
-  const int tmax = nlists * k_in;
-  const int PK = next_pow2(k_out);
-  RA_REQUIRE(tmax <= 16384 && PK <= 2048, "merge_topk_keys: nlists*k_in=%d exceeds 16384", tmax);
-  const size_t smem = (size_t)(tmax + PK) * 8;
-  RA_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 2048) * 8));
-  merge_keys_kernel<<<nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(keys, nlists, nq, k_in, k_out, PK, tmax,
-                                                                      out_scores, out_ids);
+  const size_t smem = (size_t)nlists * k_in * 8;
+  RA_REQUIRE(smem <= 200 * 1024, "merge_topk_keys: nlists*k_in=%d too large", nlists * k_in);
+  if (smem > 48 * 1024)
+    RA_CUDA(cudaFuncSetAttribute(merge_sorted_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_sorted_keys_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(base, stride_g, ptrs, nlists, nq, k_in, k_out,
+                                                                   out_scores, out_ids);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
+}
+
+extern "C" int ragarc_merge_topk_keys(const uint64_t* keys, int nlists, int nq, int k_in, int k_out,
+                                      float* out_scores, int64_t* out_ids, void* stream) {
+  RA_REQUIRE(keys, "merge_topk_keys: null keys");
+  return merge_sorted_launch(keys, (size_t)nq * k_in, nullptr, nlists, nq, k_in, k_out, out_scores, out_ids, stream);
+}
+
+extern "C" int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int nlists, int nq, int k_in, int k_out,
+                                          float* out_scores, int64_t* out_ids, void* stream) {
+  RA_REQUIRE(key_ptrs, "merge_topk_keys_p2p: null pointer table");
+  return merge_sorted_launch(nullptr, 0, key_ptrs, nlists, nq, k_in, k_out, out_scores, out_ids, stream);
 }

@@ -136,6 +136,23 @@ def merge_topk_keys(keys: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch
     return scores, ids
 
 
+def merge_topk_keys_p2p(ptr_table: torch.Tensor, nq: int, k_in: int, k_out: int,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """ptr_table: int64 device tensor of G pointers to [nq,k_in] key blocks (local or peer memory)."""
+    _cuda(ptr_table, "ptr_table")
+    dev = ptr_table.device
+    if out is None:
+        scores = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    else:
+        scores, ids = out
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_merge_topk_keys_p2p(ptr_table.data_ptr(), ptr_table.numel(), nq, k_in, k_out,
+                                                 scores.data_ptr(), ids.data_ptr(), _stream_ptr(dev)),
+                "merge_topk_keys_p2p")
+    return scores, ids
+
+
 def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
     """index: object with device tensors indptr/post_doc/post_tf/idf/doc_norm and k1_plus_1, n_docs."""
     _cuda(q_terms, "q_terms"); _cuda(q_len, "q_len")

@@ -2,17 +2,27 @@
 
 The flat index shards naturally: GPU g holds the contiguous rows ``[g*ceil(N/G), (g+1)*ceil(N/G))``
 of the corpus, every rank scores the full (replicated) query batch against its shard with
-``ragarc_dense_topk_keys`` - which already emits packed sortable keys carrying GLOBAL row ids -
-the ``[nq,k]`` key blocks are exchanged with ONE ``all_gather`` (NCCL over NVLink/NVSwitch;
-``nq*k*8`` bytes per rank, latency- not bandwidth-bound) and every rank merges the ``G*k``
-candidates per query with ``ragarc_merge_topk_keys``.  Because keys order by (score, lowest global
-row id), the result is bit-identical for any G, including G=1.
+``ragarc_dense_topk_keys`` - which already emits packed sortable keys carrying GLOBAL row ids,
+sorted per query - and the ``G`` per-shard lists of each query are merged on every rank.  Because
+keys order by (score, lowest global row id), the result is bit-identical for any G, including G=1.
+
+Two exchange paths for the ``[nq,k]`` key blocks (``nq*k*8`` bytes per rank: latency-, not
+bandwidth-bound on NVSwitch):
+
+* **peer memory** (default when it can be set up): every rank writes its keys into a buffer
+  allocated as symmetric memory, one device-side barrier orders the writes, and the merge kernel
+  (``ragarc_merge_topk_keys_p2p``) loads the other ranks' lists straight over NVLink through a table
+  of peer pointers - the gather is fused into the merge, no collective call on the data path.
+  Buffers are double-buffered so that one barrier per search suffices (a rank that passes the
+  barrier of search i+1 knows every rank has finished reading search i's buffer).
+* **NCCL**: one ``all_gather_into_tensor`` followed by ``ragarc_merge_topk_keys``.
 
 The reference has no distributed code at all; this is the multi-GPU form of
 ``faiss.IndexFlatIP.search`` (VectorStore_Faiss.py:263).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -27,28 +37,87 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_total, lo + per)
 
 
+class _PeerExchange:
+    """Symmetric-memory key buffers + peer pointer tables for one (nq, k) shape."""
+
+    def __init__(self, nq: int, k: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.nq, self.k = nq, k
+        self.buf = symm_mem.empty((2, nq, k), dtype=torch.int64, device=device)
+        grp = group if group is not None else dist.group.WORLD
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        slot_bytes = nq * k * 8
+        self.tables = [torch.tensor([p + s * slot_bytes for p in ptrs], dtype=torch.int64, device=device)
+                       for s in range(2)]
+        self.step = 0
+
+    def exchange_and_merge(self, write_keys, k_out: int):
+        slot = self.step & 1
+        self.step += 1
+        write_keys(self.buf[slot])                 # this rank's keys -> its symmetric buffer
+        self.hdl.barrier(channel=slot)             # everybody's keys of this search are in place
+        return ops.merge_topk_keys_p2p(self.tables[slot], self.nq, self.k, k_out)
+
+
 class ShardedFlatIndex:
-    def __init__(self, rows: torch.Tensor, id_base: int, n_rows: Optional[int] = None, group=None):
+    def __init__(self, rows: torch.Tensor, id_base: int, n_rows: Optional[int] = None, group=None,
+                 exchange: str = "auto"):
         """rows: this rank's shard ``[n_local(+spare), d]`` (normalised, storage dtype, on this
-        rank's GPU); id_base: global row id of ``rows[0]``."""
+        rank's GPU); id_base: global row id of ``rows[0]``; exchange: "auto" | "peer" | "nccl"."""
         self.rows = rows
         self.id_base = int(id_base)
         self.n_local = rows.shape[0] if n_rows is None else int(n_rows)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = os.environ.get("RAGARC_EXCHANGE", exchange)
         self._gather_buf = None
+        self._peer = {}
+        self._peer_failed = False
+        self.exchange_used = "none" if self.world == 1 else "nccl"
+
+    def _peer_exchange(self, nq: int, k: int):
+        key = (nq, k)
+        px = self._peer.get(key)
+        if px is None and not self._peer_failed:
+            err = None
+            try:
+                px = _PeerExchange(nq, k, self.rows.device, self.group)
+            except Exception as exc:  # noqa: BLE001 - symmetric memory not available on this system
+                if self.exchange == "peer":
+                    raise
+                err, px = exc, None
+            # all ranks must agree on the path: if any rank failed, everyone uses NCCL
+            ok = torch.tensor([1 if px is not None else 0], device=self.rows.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                px, self._peer_failed = None, True
+                if self.rank == 0:
+                    print(f"[rag_arc_b200.sharded] peer-memory exchange unavailable "
+                          f"({type(err).__name__ if err else 'peer rank'}: {err}); using NCCL all-gather")
+            self._peer[key] = px
+        return px
 
     def search(self, queries: torch.Tensor, k: int):
         """queries: ``[nq,d]`` prepared (normalised, storage dtype), identical on every rank.
         Returns ``(scores float32 [nq,k], global rows int64 [nq,k])`` on every rank."""
         nq = queries.shape[0]
-        keys = ops.dense_topk_keys(self.rows, queries, k, id_base=self.id_base, n_rows=self.n_local)
         if self.world == 1:
+            keys = ops.dense_topk_keys(self.rows, queries, k, id_base=self.id_base, n_rows=self.n_local)
             return ops.merge_topk_keys(keys.view(1, nq, k), k)
+        if self.exchange in ("auto", "peer") and queries.is_cuda:
+            px = self._peer_exchange(nq, k)
+            if px is not None:
+                self.exchange_used = "peer"
+                return px.exchange_and_merge(
+                    lambda out: ops.dense_topk_keys(self.rows, queries, k, id_base=self.id_base,
+                                                    n_rows=self.n_local, out=out), k)
+        keys = ops.dense_topk_keys(self.rows, queries, k, id_base=self.id_base, n_rows=self.n_local)
         buf = self._gather_buf
         if buf is None or buf.shape != (self.world, nq, k) or buf.device != keys.device:
             buf = torch.empty((self.world, nq, k), dtype=torch.int64, device=keys.device)
             self._gather_buf = buf
         dist.all_gather_into_tensor(buf.view(-1), keys.view(-1), group=self.group)
+        self.exchange_used = "nccl"
         return ops.merge_topk_keys(buf, k)
