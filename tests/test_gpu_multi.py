@@ -1,0 +1,58 @@
+"""GPU, >= 2 devices: row-sharded search with both key-exchange paths (peer memory over NVLink and
+NCCL all-gather) must equal the single-GPU result bit for bit.  Skipped on single-GPU boxes."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, exchange, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from rag_arc_b200 import ops, sharded, synth
+    n, d, nq, k = 300_001, 128, 200, 50
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=3)        # same corpus on every rank
+    q, _ = synth.dense_queries_cuda(x, nq, seed=4)
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    idx = sharded.ShardedFlatIndex(x[lo:hi].contiguous(), lo, exchange=exchange)
+    ok = True
+    for it in range(3):                                                     # exercises both buffer slots
+        s, i = idx.search(q, k)
+        s_ref, i_ref = ops.dense_topk(x, q, k)
+        ok = ok and bool(torch.equal(i, i_ref) and torch.equal(s, s_ref))
+    flag = torch.tensor([1 if ok and idx.exchange_used == exchange else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put((int(flag.item()), idx.exchange_used))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_sharded_search_equals_single_gpu(exchange):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    ok, used = out.get()
+    assert ok == 1, f"mismatch (exchange used: {used})"
