@@ -233,10 +233,25 @@ def run_ours(args):
     from rag_arc_b200.sharded import ShardedFlatIndex
     sharded = ShardedFlatIndex(x, lo, n_local) if world > 1 else None
 
-    def step_device():
+    def step_eager():
         if world == 1:
             return ops.dense_topk(x, q_dev, TOPK, n_rows=n_local)
         return sharded.search(q_dev, TOPK)
+
+    # the step (4 kernels, + exchange and merge for N > 1) is captured in a CUDA graph: at small
+    # shards host launch overhead is a visible fraction of the step.  --no-graph runs it eagerly.
+    step_device, graphed = step_eager, False
+    if not args.no_graph:
+        try:
+            if world == 1:
+                replay, _, _ = store.index.capture_search(q_dev, TOPK)
+            else:
+                replay, _, _ = sharded.capture(q_dev, TOPK)
+            step_device, graphed = replay, True
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
 
     res_scores_host = torch.empty((BATCH, TOPK), dtype=torch.float32).pin_memory()
     res_ids_host = torch.empty((BATCH, TOPK), dtype=torch.int64).pin_memory()
@@ -272,8 +287,18 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # per-kernel times come from a few eager steps with CUDA events inside the library (events cannot
+    # be read out of a replayed graph); the timed region below then runs undisturbed
     N.profile_enable(True)
     N.profile_read()
+    l0 = N.launch_count()
+    for _ in range(8):                      # even: keeps the peer-exchange buffer slots alternating
+        step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = (N.launch_count() - l0) // 8
+    seed_ms, score_ms, merge_ms, nrec = N.profile_read()
+    N.profile_enable(False)
+    barrier()
     launches0 = N.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -283,9 +308,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = N.launch_count() - launches0
-    seed_ms, score_ms, merge_ms, nrec = N.profile_read()
-    N.profile_enable(False)
+    launches = (N.launch_count() - launches0) if not graphed else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     qps = args.steps * BATCH / (ms_total * 1e-3)
 
@@ -386,6 +409,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "rows": N_ROWS, "dim": DIM, "batch": BATCH, "k": TOPK,
                    "rows_per_gpu": n_local, "parallelism": (f"row-shard x{world}, key exchange: {sharded.exchange_used}, merge on every rank"
                                    if world > 1 else "single GPU"),
+                   "cuda_graph": graphed,
                    "l2_policy": f"inputs larger than L2 ({n_local * DIM * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIM * 4,
                 "d2h_bytes_per_step": BATCH * TOPK * 12, "ms_per_step": e2e_ms / args.steps,
@@ -410,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     args = ap.parse_args()

@@ -104,6 +104,22 @@ class FlatIndexB200:
     def search_device(self, q_prepared: torch.Tensor, k: int):
         return ops.dense_topk(self.rows, q_prepared, k, n_rows=self.ntotal)
 
+    def capture_search(self, queries: torch.Tensor, k: int):
+        """CUDA-graph ``search_device`` for a fixed, already prepared query buffer: returns
+        ``(replay, scores, rows)``; refill ``queries`` in place, call ``replay()``."""
+        self.search_device(queries, k)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.search_device(queries, k)         # workspace of the capture stream exists now
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                scores, rows = self.search_device(queries, k)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return g.replay, scores, rows
+
     def search(self, q, k: int):
         """faiss-style: numpy in, ``(D float32 [nq,k], I int64 [nq,k])`` numpy out."""
         D, I = self.search_device(self.prepare_queries(q), k)
@@ -286,6 +302,36 @@ class B200VectorStore(VectorStore):
         D = D.cpu().numpy(); I = I.cpu().numpy()
         return [[(self.docstore[self.index_to_docstore_id[int(r)]], float(s)) for s, r in zip(Dq, Iq) if r != -1]
                 for Dq, Iq in zip(D, I)]
+
+    def self_join(self, k: int = 10, min_score: Optional[float] = None, batch: int = 4096):
+        """All-pairs nearest neighbours inside the store (the cosine self-join the reference does
+        with an O(n^2) host matrix for entity dedup / event KNN: Base_Neo4j.py:538-590 uses
+        sklearn cosine >= 0.95, event_graphrag_neo4j.py:637-648 a top-10 KNN with cutoff 0.85).
+        Every stored row is used as a query against the whole matrix, ``batch`` rows at a time.
+        Returns ``(scores float32 [n,k], rows int64 [n,k])`` on the device with the self match
+        removed; entries below ``min_score`` are set to (-inf, -1)."""
+        if self.ntotal == 0:
+            raise ValueError("the store is empty")
+        n = self.ntotal
+        kk = min(k + 1, n)
+        out_s = torch.full((n, k), float("-inf"), dtype=torch.float32, device=self.device)
+        out_r = torch.full((n, k), -1, dtype=torch.int64, device=self.device)
+        for s0 in range(0, n, batch):
+            e0 = min(n, s0 + batch)
+            sc, rw = ops.dense_topk(self.index.rows, self.index.rows[s0:e0].contiguous(), kk, n_rows=n)
+            me = torch.arange(s0, e0, device=self.device)[:, None]
+            keep = rw != me
+            # drop exactly one entry per row: the self match if present, else the last one
+            none = keep.all(dim=1)
+            keep[none, kk - 1] = False
+            idx = keep.float().argsort(dim=1, descending=True, stable=True)[:, :kk - 1]
+            sc = sc.gather(1, idx); rw = rw.gather(1, idx)
+            if min_score is not None:
+                bad = sc < min_score
+                sc = sc.masked_fill(bad, float("-inf")); rw = rw.masked_fill(bad, -1)
+            out_s[s0:e0, :kk - 1] = sc
+            out_r[s0:e0, :kk - 1] = rw
+        return out_s, out_r
 
     def rows_to_documents(self, rows: Sequence[int]) -> List[Document]:
         return [self.docstore[self.index_to_docstore_id[int(r)]] for r in rows if r != -1]

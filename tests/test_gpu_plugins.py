@@ -114,6 +114,23 @@ def test_search_pipeline_equals_synchronous_search(dev):
         pipe.submit(torch.zeros((3, 64)))
 
 
+def test_self_join_matches_bruteforce(dev):
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((3000, 64)).astype(np.float32)
+    base[100] = base[7] + 1e-3 * rng.standard_normal(64)          # a near-duplicate pair
+    store = B200VectorStore.from_embeddings([str(i) for i in range(3000)], base, metric="cosine", device=dev)
+    sc, rw = store.self_join(k=5, min_score=None, batch=1024)
+    X = base / np.linalg.norm(base, axis=1, keepdims=True)
+    S = X.astype(np.float64) @ X.astype(np.float64).T
+    np.fill_diagonal(S, -np.inf)
+    want = np.argsort(-S, axis=1)[:, :5]
+    assert (rw.cpu().numpy() == want).mean() > 0.999                # fp32 ties aside
+    assert rw[7, 0].item() == 100 and rw[100, 0].item() == 7
+    assert not (rw == torch.arange(3000, device=dev)[:, None]).any()
+    sc2, rw2 = store.self_join(k=5, min_score=0.95)
+    assert (rw2[7] >= 0).sum().item() == 1 and rw2[7, 0].item() == 100 and (rw2[8] == -1).all()
+
+
 def _bm25_fixture():
     with open(os.path.join(GOLD, "bm25_hybrid_small.json")) as f:
         return json.load(f)
