@@ -242,16 +242,22 @@ def run_ours(args):
     # shards host launch overhead is a visible fraction of the step.  --no-graph runs it eagerly.
     step_device, graphed = step_eager, False
     if not args.no_graph:
+        replay = None
         try:
             if world == 1:
                 replay, _, _ = store.index.capture_search(q_dev, TOPK)
             else:
                 replay, _, _ = sharded.capture(q_dev, TOPK)
-            step_device, graphed = replay, True
         except Exception as exc:  # noqa: BLE001
+            replay = None
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
             torch.cuda.synchronize()
+        ok = torch.tensor([1 if replay is not None else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank replays, or none does
+        if int(ok.item()) == 1:
+            step_device, graphed = replay, True
 
     res_scores_host = torch.empty((BATCH, TOPK), dtype=torch.float32).pin_memory()
     res_ids_host = torch.empty((BATCH, TOPK), dtype=torch.int64).pin_memory()
