@@ -73,6 +73,20 @@ def dense_case(name, n, d, dtype, nq, k, dev, iters=20):
     torch.cuda.empty_cache()
 
 
+def x3_case(dev):
+    """fp32 storage, 100k x 768, batch 256: CUDA-core fp32 path vs bf16x3 tensor-core path."""
+    n, d, nq, k = 100_000, 768, 256, 50
+    X = torch.from_numpy(synth.dense_corpus_np(n, d)).to(dev)
+    q, _ = synth.dense_queries_cuda(X, nq)
+    xp = ops.normalize_split3(X, False); qp = ops.normalize_split3(q, False)
+    m_simt, _ = timeit(lambda: ops.dense_topk(X, q, k), 5)
+    m_x3, _ = timeit(lambda: ops.dense_topk_x3(xp, qp, k), 20)
+    s1, i1 = ops.dense_topk(X, q, k); s2, i2 = ops.dense_topk_x3(xp, qp, k)
+    emit(config="fp32-100kx768-Q256", ms_simt=m_simt, ms_bf16x3=m_x3, speedup=m_simt / m_x3,
+         ids_equal=float((i1 == i2).float().mean()), max_abs_score_diff=float((s1 - s2).abs().max()),
+         eff_tflops_x3=2.0 * nq * n * d / (m_x3 * 1e-3) / 1e12)
+
+
 def c2_hybrid(dev):
     n, d, nq, k = 100_000, 768, 256, 50
     toks, offs = synth.bm25_corpus_tokens(n)
@@ -137,6 +151,8 @@ def main():
     if on("c5"):
         for nq in (1, 8, 64):
             dense_case(f"C5-shard(G=8)-Q{nq}", 6_250_000, 768, torch.bfloat16, nq, 100, dev, iters=10)
+    if on("x3"):
+        x3_case(dev)
     if on("simt"):
         dense_case("fp32-100kx768-Q256", 100_000, 768, torch.float32, 256, 50, dev, iters=5)
 

@@ -87,6 +87,20 @@ int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const voi
                       int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
                       size_t workspace_bytes, int path, int* path_used_host, void* stream);
 
+/* fp32-accurate search on the tensor cores ("bf16x3").  An fp32 vector v is stored as three bf16
+ * planes v1+v2+v3 (v1 = bf16(v), v2 = bf16(v-v1), v3 = bf16(v-v1-v2); exact to 2^-24 relative), a
+ * row being [v1 | v2 | v3] (3*d bf16).  The inner product is accumulated in fp32 over the six
+ * largest plane-pair products - six passes of the bf16 kernel - and matches the fp32 inner product
+ * the reference computes (IndexFlatIP holds fp32, VectorStore_Faiss.py:170) to ~1e-6, at 1/6 of the
+ * bf16 rate instead of CUDA-core rate.  d must be a multiple of 64.
+ * ragarc_normalize_split3: fp32 [n,d] -> (optionally L2-normalised, faiss semantics) planes [n,3d]. */
+int ragarc_normalize_split3(const float* src, void* dst_planes, int64_t n, int d, int normalize,
+                            void* stream);
+size_t ragarc_dense_topk_x3_workspace_bytes(int64_t n, int d, int nq, int k);
+int ragarc_dense_topk_x3(const void* corpus_planes, int64_t n, int d, const void* query_planes,
+                         int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Same search, but returns packed sortable keys for the multi-GPU merge:
  *   key = (orderable_fp32(score) << 32) | (0xFFFFFFFF - (id_base + row)),  0 = empty slot,
  * sorted descending per query.  One shard per GPU; id_base = first global row of the shard. */

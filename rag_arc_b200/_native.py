@@ -25,6 +25,7 @@ EXPORTS = [
     "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
     "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk", "ragarc_dense_topk_keys",
+    "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
 ]
@@ -74,6 +75,9 @@ def _load():
                                       c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P,
                                            c_size_t, c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_normalize_split3": (c_int, [P, P, c_int64, c_int, c_int, P]),
+        "ragarc_dense_topk_x3_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+        "ragarc_dense_topk_x3": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, c_size_t, P]),
         "ragarc_merge_topk_keys": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_merge_topk_keys_p2p": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_bm25_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -139,8 +139,9 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
 static int dense_common(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                         int k, uint64_t id_base, uint64_t* out_keys, float* out_scores,
                         int64_t* out_ids, void* workspace, size_t workspace_bytes, int path,
-                        int* path_used_host, cudaStream_t stream) {
+                        int* path_used_host, cudaStream_t stream, int x3_d = 0) {
   DensePlan pl;
+  pl.x3_d = x3_d;
   int use = 0;
   if (path == RAGARC_DENSE_AUTO && !dense_tc_supported(corpus, n, d, dtype, queries)) path = RAGARC_DENSE_SIMT;
   int rc = plan_dense(n, d, dtype, nq, k, path, &pl, &use);
@@ -225,6 +226,23 @@ int ragarc_profile_read(double* seed_ms_sum_host, double* score_ms_sum_host, dou
   if (merge_ms_sum_host) *merge_ms_sum_host = b;
   if (n_host) *n_host = (int)recs.size();
   return RAGARC_OK;
+}
+
+size_t ragarc_dense_topk_x3_workspace_bytes(int64_t n, int d, int nq, int k) {
+  DensePlan pl;
+  int use;
+  if (d % 64 != 0) return 0;
+  if (plan_dense(n, 3 * d, RAGARC_BF16, nq, k, RAGARC_DENSE_TCGEN05, &pl, &use) != RAGARC_OK) return 0;
+  return pl.total;
+}
+
+int ragarc_dense_topk_x3(const void* corpus_planes, int64_t n, int d, const void* query_planes, int nq, int k,
+                         float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  RA_REQUIRE(out_scores && out_ids, "dense_topk_x3: null outputs");
+  RA_REQUIRE(d > 0 && d % 64 == 0, "dense_topk_x3: d=%d must be a multiple of 64", d);
+  return dense_common(corpus_planes, n, 3 * d, RAGARC_BF16, query_planes, nq, k, 0, nullptr, out_scores, out_ids,
+                      workspace, workspace_bytes, RAGARC_DENSE_TCGEN05, nullptr, (cudaStream_t)stream, d);
 }
 
 size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k) {

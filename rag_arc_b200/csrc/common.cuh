@@ -314,6 +314,7 @@ struct DensePlan {
   int keep;            // a list longer than this is pruned to k at item end (S*keep <= 8192)
   int seed_rows;       // >0: thresholds are seeded from exact scores of the first seed_rows rows
   int seed_S;          // corpus slices of the seed pass
+  int x3_d;            // >0: rows are three bf16 planes [x1|x2|x3] of a d=x3_d fp32 vector (width 3*x3_d)
   size_t off_lists, off_counts, off_gthr, off_keys, off_qpad, off_seed, total;
 };
 

@@ -155,6 +155,7 @@ struct Params {
   uint64_t* lists;
   int* counts;
   uint32_t* gthr;
+  int kb_per_plane;    // >0: bf16x3 split operands, k blocks per plane (see launch_dense_tc)
   int prefetch;        // RAGARC_TC_PREFETCH: L2 prefetch distance in tiles (0 = off; measured 2 % slower when on)
   float* seed_out;     // MODE_STORE: [nq, seed_ld] maxima of 16-row groups of rows [0, n)
   int seed_ld;
@@ -227,8 +228,16 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a = tiles_smem + stage * STAGE_BYTES;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);   // both CTAs' bytes
-            tma_load_2d<CG>(a, &tmap_q, &full_bar[stage], kb * BK, q0);
-            tma_load_2d<CG>(a + A_BYTES, &tmap_x, &full_bar[stage], kb * BK, x0);
+            int ka = kb * BK, kx = kb * BK;
+            if (p.kb_per_plane) {
+              // bf16x3: k block kb belongs to plane pair (query plane, corpus plane), smallest terms first:
+              // (1,1) (0,2) (2,0) (0,1) (1,0) (0,0)
+              const int pair = kb / p.kb_per_plane, kk = kb - pair * p.kb_per_plane;
+              ka = (((0x010201 >> (4 * pair)) & 0xF) * p.kb_per_plane + kk) * BK;
+              kx = (((0x001021 >> (4 * pair)) & 0xF) * p.kb_per_plane + kk) * BK;
+            }
+            tma_load_2d<CG>(a, &tmap_q, &full_bar[stage], ka, q0);
+            tma_load_2d<CG>(a + A_BYTES, &tmap_x, &full_bar[stage], kx, x0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -458,7 +467,11 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   rc = make_map(&mx, corpus, n, d, dtype, BN / cg);
   if (rc) return rc;
   Params p;
-  p.n = n; p.nq = nq; p.k = k; p.num_kb = (d + BK - 1) / BK; p.MB = pl.MB; p.S = pl.S;
+  p.n = n; p.nq = nq; p.k = k; p.MB = pl.MB; p.S = pl.S;
+  // bf16x3: an fp32 vector v is stored as three bf16 planes v1+v2+v3 (width d = 3*x3_d); the dot
+  // product is the sum of the six largest plane-pair products, i.e. six passes over x3_d
+  p.kb_per_plane = pl.x3_d > 0 ? pl.x3_d / BK : 0;
+  p.num_kb = pl.x3_d > 0 ? 6 * p.kb_per_plane : (d + BK - 1) / BK;
   p.tiles = pl.tiles; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
   p.seed_out = nullptr; p.seed_ld = 0;
   {

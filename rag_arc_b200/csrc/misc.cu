@@ -44,6 +44,31 @@ __global__ void normalize_cast_kernel(const float* __restrict__ src, T* __restri
   for (int i = lane; i < d; i += 32) o[i] = from_f32<T>(__fmul_rn(s[i], scale));
 }
 
+// ---- normalize + split into three bf16 planes: v = b1 + b2 + b3 up to 2^-24 relative ------------
+__global__ void normalize_split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
+                                        int d, int normalize) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = src + (size_t)row * d;
+  __nv_bfloat16* o = dst + (size_t)row * 3 * d;
+  float scale = 1.0f;
+  if (normalize) {
+    float nr = 0.f;
+    for (int i = lane; i < d; i += 32) { float v = s[i]; nr = fmaf(v, v, nr); }
+    nr = warp_sum(nr);
+    if (nr > 0.f) scale = __fdiv_rn(1.0f, __fsqrt_rn(nr));
+  }
+  for (int i = lane; i < d; i += 32) {
+    const float v = __fmul_rn(s[i], scale);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(b1);          // exact
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b2);         // exact
+    o[i] = b1; o[d + i] = b2; o[2 * d + i] = __float2bfloat16_rn(r2);
+  }
+}
+
 // ---- pool + normalize: one CTA per sequence ---------------------------------------------------
 // HBM-bound: every kept token row is read once.  The CTA is a (TS token-slices) x (column groups)
 // grid of threads; a thread owns VEC consecutive columns (one 16-byte load per token) and sums the
@@ -290,6 +315,17 @@ int ragarc_normalize_cast(const float* src, void* dst, int64_t n, int d, int dst
   else if (dst_dtype == RAGARC_BF16) normalize_cast_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>(src, (__nv_bfloat16*)dst, n, d, normalize);
   else if (dst_dtype == RAGARC_F16) normalize_cast_kernel<__half><<<grid, warps * 32, 0, st>>>(src, (__half*)dst, n, d, normalize);
   else { set_error("normalize_cast: bad dtype %d", dst_dtype); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_normalize_split3(const float* src, void* dst, int64_t n, int d, int normalize, void* stream) {
+  RA_REQUIRE(n >= 0 && d > 0, "normalize_split3: bad shape n=%lld d=%d", (long long)n, d);
+  if (n == 0) return RAGARC_OK;
+  RA_REQUIRE(src && dst, "normalize_split3: null pointer");
+  const int warps = 8;
+  normalize_split3_kernel<<<(unsigned)ceil_div(n, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)dst, n, d, normalize);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

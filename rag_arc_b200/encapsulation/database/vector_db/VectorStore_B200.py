@@ -38,7 +38,13 @@ _DTYPES = {"float32": torch.float32, "fp32": torch.float32, "bfloat16": torch.bf
            "float16": torch.float16, "fp16": torch.float16}
 
 
+def _is_x3(dt) -> bool:
+    return isinstance(dt, str) and dt.lower() in ("float32x3", "fp32x3", "bf16x3")
+
+
 def _as_dtype(dt) -> torch.dtype:
+    if _is_x3(dt):
+        return torch.float32
     if isinstance(dt, torch.dtype):
         if dt not in ops._DT:
             raise ValueError(f"unsupported storage dtype: {dt}")
@@ -53,7 +59,7 @@ class FlatIndexB200:
     """The slice of the ``faiss.IndexFlatIP`` API the reference uses (``d``, ``ntotal``,
     ``is_trained``, ``add``, ``reset``, ``search``) over a device-resident matrix."""
 
-    def __init__(self, d: int, dtype: torch.dtype, device, normalize: bool):
+    def __init__(self, d: int, dtype: torch.dtype, device, normalize: bool, x3: bool = False):
         self.d = int(d)
         self.dtype = dtype
         self.device = torch.device(device)
@@ -61,6 +67,9 @@ class FlatIndexB200:
         self.is_trained = True
         self.ntotal = 0
         self.rows = torch.empty((0, self.d), dtype=dtype, device=self.device)
+        # "float32x3": fp32 master rows + three bf16 planes per row for fp32-accurate tensor-core search
+        self.x3 = bool(x3)
+        self.planes = torch.empty((0, 3 * self.d), dtype=torch.bfloat16, device=self.device) if x3 else None
 
     def _reserve(self, need: int) -> None:
         cap = self.rows.shape[0]
@@ -71,6 +80,11 @@ class FlatIndexB200:
         if self.ntotal:
             grown[:self.ntotal].copy_(self.rows[:self.ntotal])
         self.rows = grown
+        if self.x3:
+            gp = torch.empty((new_cap, 3 * self.d), dtype=torch.bfloat16, device=self.device)
+            if self.ntotal:
+                gp[:self.ntotal].copy_(self.planes[:self.ntotal])
+            self.planes = gp
 
     def add(self, x) -> None:
         """x: fp32 [n,d] numpy array or tensor (host or device); normalised (if the store's metric
@@ -82,6 +96,8 @@ class FlatIndexB200:
         n = xt.shape[0]
         self._reserve(self.ntotal + n)
         ops.normalize_cast(xt, self.dtype, self.normalize, out=self.rows[self.ntotal:self.ntotal + n])
+        if self.x3:
+            ops.normalize_split3(xt, self.normalize, out=self.planes[self.ntotal:self.ntotal + n])
         self.ntotal += n
 
     def add_prepared(self, rows: torch.Tensor) -> None:
@@ -89,6 +105,9 @@ class FlatIndexB200:
         n = rows.shape[0]
         self._reserve(self.ntotal + n)
         self.rows[self.ntotal:self.ntotal + n].copy_(rows)
+        if self.x3:
+            ops.normalize_split3(rows.to(torch.float32).contiguous(), False,
+                                 out=self.planes[self.ntotal:self.ntotal + n])
         self.ntotal += n
 
     def reset(self) -> None:
@@ -99,9 +118,13 @@ class FlatIndexB200:
         if qt.dim() == 1:
             qt = qt[None, :]
         qt = qt.to(device=self.device, dtype=torch.float32).contiguous()
+        if self.x3:
+            return ops.normalize_split3(qt, self.normalize)
         return ops.normalize_cast(qt, self.dtype, self.normalize)
 
     def search_device(self, q_prepared: torch.Tensor, k: int):
+        if self.x3:
+            return ops.dense_topk_x3(self.planes, q_prepared, k, n_rows=self.ntotal)
         return ops.dense_topk(self.rows, q_prepared, k, n_rows=self.ntotal)
 
     def capture_search(self, queries: torch.Tensor, k: int):
@@ -145,9 +168,6 @@ class SearchPipeline:
         for _ in range(depth):
             self.slots.append({
                 "q32": torch.empty((nq, index.d), dtype=torch.float32, device=dev),
-                "q": torch.empty((nq, index.d), dtype=index.dtype, device=dev),
-                "scores": torch.empty((nq, k), dtype=torch.float32, device=dev),
-                "rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
                 "h_scores": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                 "h_rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
                 "copied_in": torch.cuda.Event(), "computed": torch.cuda.Event(), "copied_out": torch.cuda.Event(),
@@ -170,14 +190,13 @@ class SearchPipeline:
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(slot["copied_in"])
             self.s_cmp.wait_event(slot["copied_out"])         # previous results of this slot have left
-            ops.normalize_cast(slot["q32"], self.index.dtype, self.index.normalize, out=slot["q"])
-            ops.dense_topk(self.index.rows, slot["q"], self.k, n_rows=self.index.ntotal,
-                           out=(slot["scores"], slot["rows"]))
+            slot["scores"], slot["rows"] = self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
             slot["computed"].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
             slot["h_scores"].copy_(slot["scores"], non_blocking=True)
             slot["h_rows"].copy_(slot["rows"], non_blocking=True)
+            slot["scores"].record_stream(self.s_out); slot["rows"].record_stream(self.s_out)
             slot["copied_out"].record(self.s_out)
         slot["busy"] = True
         self.n_submitted += 1
@@ -201,6 +220,7 @@ class B200VectorStore(VectorStore):
         self.normalize_L2 = normalize_L2
         self.index = index
         self.dtype = _as_dtype(dtype)
+        self.x3 = _is_x3(dtype)
         self.device = torch.device(device)
         self.docstore: dict[str, Document] = {}
         self.index_to_docstore_id: dict[int, str] = {}
@@ -218,7 +238,9 @@ class B200VectorStore(VectorStore):
             raise ValueError(f"unsupported index type: {self.index_type} (B200VectorStore is exact/flat only)")
         if self.metric == "l2":
             raise ValueError("metric 'l2' is not offered by B200VectorStore (inner product / cosine only)")
-        return FlatIndexB200(dimension, self.dtype, self.device, self._normalizes())
+        if self.x3 and dimension % 64 != 0:
+            raise ValueError("dtype 'float32x3' needs an embedding dimension that is a multiple of 64")
+        return FlatIndexB200(dimension, self.dtype, self.device, self._normalizes(), x3=self.x3)
 
     def _normalizes(self) -> bool:
         return bool(self.normalize_L2 or self.metric == "cosine")
@@ -318,7 +340,10 @@ class B200VectorStore(VectorStore):
         out_r = torch.full((n, k), -1, dtype=torch.int64, device=self.device)
         for s0 in range(0, n, batch):
             e0 = min(n, s0 + batch)
-            sc, rw = ops.dense_topk(self.index.rows, self.index.rows[s0:e0].contiguous(), kk, n_rows=n)
+            if self.index.x3:
+                sc, rw = ops.dense_topk_x3(self.index.planes, self.index.planes[s0:e0].contiguous(), kk, n_rows=n)
+            else:
+                sc, rw = ops.dense_topk(self.index.rows, self.index.rows[s0:e0].contiguous(), kk, n_rows=n)
             me = torch.arange(s0, e0, device=self.device)[:, None]
             keep = rw != me
             # drop exactly one entry per row: the self match if present, else the last one
@@ -353,6 +378,9 @@ class B200VectorStore(VectorStore):
         _, cand = self.index.search_device(q, fetch)
         if k >= fetch:
             return self.rows_to_documents(cand[0].tolist())
+        if self.index.x3:      # MMR works on the fp32 master rows
+            q = ops.normalize_cast(torch.as_tensor(np.asarray([embedding], dtype=np.float32)).to(self.device),
+                                   torch.float32, self.index.normalize)
         sel = ops.mmr_select(self.index.rows, q, cand.contiguous(), k, lambda_mult, n_rows=self.ntotal)
         cand_h = cand[0].tolist()
         return self.rows_to_documents([cand_h[j] for j in sel[0].tolist() if j >= 0])
@@ -409,7 +437,7 @@ class B200VectorStore(VectorStore):
             np.save(os.path.join(folder_path, f"{index_name}.b200.npy"), host)
         side = {"docstore": self.docstore, "index_to_docstore_id": self.index_to_docstore_id,
                 "index_type": self.index_type, "metric": self.metric, "normalize_L2": self.normalize_L2,
-                "dtype": str(self.dtype).replace("torch.", "")}
+                "dtype": "float32x3" if self.x3 else str(self.dtype).replace("torch.", "")}
         with open(os.path.join(folder_path, f"{index_name}.pkl"), "wb") as fh:
             pickle.dump(side, fh)
 

@@ -104,6 +104,49 @@ def dense_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, n_rows: O
     return scores, ids
 
 
+def normalize_split3(src: torch.Tensor, normalize: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [n,d] -> three bf16 planes [n,3d] (v = v1+v2+v3 to 2^-24), optionally L2-normalised first."""
+    _cuda(src, "src")
+    if src.dtype != torch.float32 or src.dim() != 2:
+        raise N.RagArcError("normalize_split3 expects a 2-D float32 tensor")
+    n, d = src.shape
+    if out is None:
+        out = torch.empty((n, 3 * d), dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        N.check(N.lib.ragarc_normalize_split3(src.data_ptr(), out.data_ptr(), n, d, int(bool(normalize)),
+                                              _stream_ptr(src.device)), "normalize_split3")
+    return out
+
+
+def dense_topk_x3(corpus_planes: torch.Tensor, query_planes: torch.Tensor, k: int, *,
+                  n_rows: Optional[int] = None, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """fp32-accurate exact top-k on the tensor cores over bf16x3 planes ([n,3d] / [nq,3d])."""
+    _cuda(corpus_planes, "corpus_planes"); _cuda(query_planes, "query_planes")
+    if corpus_planes.dtype != torch.bfloat16 or query_planes.dtype != torch.bfloat16:
+        raise N.RagArcError("bf16x3 planes must be bfloat16")
+    n = corpus_planes.shape[0] if n_rows is None else int(n_rows)
+    d3 = corpus_planes.shape[1]
+    if d3 % 3 or query_planes.shape[1] != d3:
+        raise N.RagArcError("plane matrices must be [*, 3d] with equal d")
+    d = d3 // 3
+    nq = query_planes.shape[0]
+    dev = corpus_planes.device
+    if out is None:
+        scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    else:
+        scores, ids = out
+    wsb = int(N.lib.ragarc_dense_topk_x3_workspace_bytes(n, d, nq, k))
+    if wsb == 0:
+        raise N.RagArcError(f"bf16x3 search unsupported for d={d}, k={k}")
+    ws = _workspace(dev, wsb, "dense")
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_dense_topk_x3(corpus_planes.data_ptr(), n, d, query_planes.data_ptr(), nq, k,
+                                           scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _stream_ptr(dev)), "dense_topk_x3")
+    return scores, ids
+
+
 def dense_topk_keys(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base: int, *,
                     n_rows: Optional[int] = None, path: int = N.DENSE_AUTO,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:

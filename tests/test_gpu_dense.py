@@ -166,3 +166,22 @@ def test_full_size_properties_1m_x_768(dev):
     rows_q, cols = beats.nonzero(as_tuple=True)
     for rq, c in zip(rows_q.tolist()[:2000], cols.tolist()[:2000]):
         assert (ids[rq] == sample[c]).any()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(10_000, 384, 100, 10), (60_000, 768, 300, 100), (3000, 64, 5, 7)])
+def test_bf16x3_tensor_core_path_is_fp32_accurate(dev, n, d, nq, k):
+    """fp32 corpus, fp32 queries, searched on the tensor cores through three bf16 planes: scores
+    must match the fp32 oracle (FAISS restatement) to 1e-5 and ids exactly (tie-aware)."""
+    X = synth.dense_corpus_np(n, d, seed=31)
+    Q, planted = synth.dense_queries_np(X, nq, seed=32)
+    xp = ops.normalize_split3(torch.from_numpy(X).to(dev), normalize=False)
+    qp = ops.normalize_split3(torch.from_numpy(Q).to(dev), normalize=False)
+    # the planes reconstruct the fp32 values to 2^-24 relative
+    rec = xp.float().view(n, 3, d).sum(1).cpu().numpy()
+    assert np.abs(rec - X).max() <= 2.0 ** -22 * np.abs(X).max()
+    scores, ids = ops.dense_topk_x3(xp, qp, k)
+    _check_all(ids, scores, X, Q, k, "bf16x3")
+    assert (ids[:, 0].cpu().numpy() == planted).all()
+    D, I = odense.flat_ip_search(X, Q, k)
+    assert np.allclose(scores.cpu().numpy(), D, rtol=1e-5, atol=1e-6)
+    assert (ids.cpu().numpy() == I).mean() > 0.999
