@@ -67,8 +67,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms; started ahead of the timed region
+    (nvidia-smi takes a moment to come up), only the samples whose timestamps fall inside
+    [mark_begin(), mark_end()] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -76,11 +78,12 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -88,29 +91,41 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                except Exception:
+                    continue
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.03 <= x[0] <= (self.t1 or 1e18) + 0.06]
+        sm, mx, pw, reasons = collect(inside if len(inside) >= 2 else self.rows)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "window": "timed region" if len(inside) >= 2 else "whole run", "reasons": sorted(reasons)}
 
 
 def cpu_reference_qps(X32, Q32, k, budget_s=15.0, max_queries=None):
@@ -284,15 +299,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up ---------------------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
 
     # ---- timed region: device-resident inputs ----------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # per-kernel times come from a few eager steps with CUDA events inside the library (events cannot
     # be read out of a replayed graph); the timed region below then runs undisturbed
     N.profile_enable(True)
@@ -308,11 +323,13 @@ def run_ours(args):
     launches0 = N.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = (N.launch_count() - launches0) if not graphed else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None

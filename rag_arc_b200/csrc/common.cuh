@@ -89,9 +89,10 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
   return v;
 }
 
-// Histogram increment used by every radix-select pass.  (A __match_any_sync-aggregated variant was
-// measured slower on B200 than plain shared-memory atomics: merge 84 -> 113 us, see profiles/.)
-__device__ __forceinline__ void hist_add_agg(uint32_t* hist, uint32_t bin, bool valid) {
+// Histogram increment used by every radix-select pass: a plain shared-memory atomic.  (A
+// __match_any_sync warp-aggregated variant was measured SLOWER on B200: merge kernel 84 -> 113 us,
+// see profiles/README.md.)
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool valid) {
   if (valid) atomicAdd(&hist[bin], 1u);
 }
 
@@ -213,7 +214,7 @@ static __device__ __noinline__ uint32_t warp_prune_reg(uint64_t* __restrict__ li
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; ++j)
-      hist_add_agg(hist, (uint32_t)(key[j] >> shift) & 0xFFu, key[j] != 0ull && (key[j] & mask) == prefix);
+      hist_add(hist, (uint32_t)(key[j] >> shift) & 0xFFu, key[j] != 0ull && (key[j] & mask) == prefix);
     __syncwarp();
     uint32_t h[8], sum = 0;
 #pragma unroll

@@ -43,7 +43,7 @@ __device__ __forceinline__ void block_select_topk(const uint64_t* keys, int T, i
     for (int b = 0; b < T; b += blockDim.x) {
       const int i = b + threadIdx.x;
       const uint64_t key = i < T ? keys[i] : 0ull;
-      hist_add_agg(hist, (uint32_t)(key >> shift) & 0xFFu, i < T && (key & mask) == prefix);
+      hist_add(hist, (uint32_t)(key >> shift) & 0xFFu, i < T && (key & mask) == prefix);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -350,7 +350,7 @@ seed_select_kernel(const float* __restrict__ scores, int S, int k, uint32_t* __r
     for (int b = 0; b < S; b += blockDim.x) {
       const int i = b + threadIdx.x;
       const uint32_t o = i < S ? ords[i] : 0u;
-      hist_add_agg(hist, (o >> shift) & 0xFFu, i < S && (o & mask) == prefix);
+      hist_add(hist, (o >> shift) & 0xFFu, i < S && (o & mask) == prefix);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
