@@ -433,6 +433,7 @@ def run_ours(args):
                    "rows_per_gpu": n_local, "parallelism": (f"row-shard x{world}, key exchange: {sharded.exchange_used}, merge on every rank"
                                    if world > 1 else "single GPU"),
                    "cuda_graph": graphed,
+                   "schedule": N.dense_plan(n_local, DIM, N.BF16 if DTYPE == "bfloat16" else N.F16, BATCH, TOPK),
                    "l2_policy": f"inputs larger than L2 ({n_local * DIM * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIM * 4,
                 "d2h_bytes_per_step": BATCH * TOPK * 12, "ms_per_step": e2e_ms / args.steps,

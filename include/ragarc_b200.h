@@ -83,6 +83,11 @@ int ragarc_normalize_cast(const float* src, void* dst, int64_t n, int d, int dst
  * `path` = RAGARC_DENSE_AUTO lets the library choose; *path_used (host, may be NULL) reports it.
  */
 size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k);
+/* Introspection: the schedule the library would use for this shape (for logs and benchmarks).
+ * out[0..10) = path, query rows per work item, CTA pairs per multicast cluster, query blocks,
+ * corpus slices, resident work-item slots, seed rows, candidates kept per list, slices given to the
+ * concurrent plain-pair launch, corpus tiles given to the multicast-cluster launch. */
+int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out10);
 int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                       int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
                       size_t workspace_bytes, int path, int* path_used_host, void* stream);
@@ -126,6 +131,10 @@ int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int nlists, int 
  * indptr[V+1] (int64), post_doc/post_tf[nnz] (int32; doc ids unique inside one posting list),
  * idf[V], doc_norm[n_docs] = k1*(1-b+b*dl/avgdl) (fp64, computed by the host exactly as the
  * reference expression does), k1_plus_1 = k1+1.
+ * post_val[nnz] (fp64, may be NULL): the query-independent factor tf*(k1+1)/(tf+doc_norm[doc]) of
+ * every posting, precomputed by the host with numpy in the reference's operation order; when given,
+ * the kernels multiply it by idf[t] instead of redoing the fp64 division and the doc_norm gather
+ * per query (bit-identical either way).
  * q_terms: [nq,tmax] term ids in query order, duplicates repeated, -1 = token not in the
  * vocabulary (contributes 0) ; q_len[nq].
  * score[d] += idf[t] * ( tf*(k1+1) / (tf + doc_norm[d]) ), fp64, each operation individually
@@ -134,11 +143,11 @@ int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int nlists, int 
  */
 size_t ragarc_bm25_workspace_bytes(int64_t n_docs, int nq);
 int ragarc_bm25_scores(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
-                       const double* idf, const double* doc_norm, double k1_plus_1,
+                       const double* post_val, const double* idf, const double* doc_norm, double k1_plus_1,
                        const int32_t* q_terms, const int32_t* q_len, int nq, int tmax,
                        int64_t n_docs, double* out_scores /* [nq,n_docs] */, void* stream);
 int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
-                     const double* idf, const double* doc_norm, double k1_plus_1,
+                     const double* post_val, const double* idf, const double* doc_norm, double k1_plus_1,
                      const int32_t* q_terms, const int32_t* q_len, int nq, int tmax,
                      int64_t n_docs, int k, double* out_scores /* [nq,k] */,
                      int64_t* out_ids /* [nq,k] */, void* workspace, size_t workspace_bytes,

@@ -24,7 +24,7 @@ DENSE_AUTO, DENSE_SIMT, DENSE_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
     "ragarc_profile_read", "ragarc_normalize_cast",
-    "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk", "ragarc_dense_topk_keys",
+    "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk_plan", "ragarc_dense_topk", "ragarc_dense_topk_keys",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
@@ -71,6 +71,7 @@ def _load():
                                         ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
         "ragarc_normalize_cast": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
         "ragarc_dense_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
+        "ragarc_dense_topk_plan": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
         "ragarc_dense_topk": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, P, P, P, c_size_t,
                                       c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P,
@@ -81,8 +82,8 @@ def _load():
         "ragarc_merge_topk_keys": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_merge_topk_keys_p2p": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_bm25_workspace_bytes": (c_size_t, [c_int64, c_int]),
-        "ragarc_bm25_scores": (c_int, [P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, P, P]),
-        "ragarc_bm25_topk": (c_int, [P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
+        "ragarc_bm25_scores": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, P, P]),
+        "ragarc_bm25_topk": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
                                      P, c_size_t, P]),
         "ragarc_rrf_fuse": (c_int, [P, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),
         "ragarc_pool_normalize": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -120,6 +121,15 @@ def profile_read():
     check(lib.ragarc_profile_read(ctypes.byref(s), ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)),
           "profile_read")
     return s.value, a.value, b.value, n.value
+
+
+def dense_plan(n: int, d: int, dtype: int, nq: int, k: int, path: int = 0) -> dict:
+    """The schedule ``ragarc_dense_topk`` would use for this shape (needs the current CUDA device)."""
+    out = (ctypes.c_int * 10)()
+    check(lib.ragarc_dense_topk_plan(n, d, dtype, nq, k, path, out), "dense_topk_plan")
+    keys = ("path", "rows_per_item", "pairs_per_cluster", "query_blocks", "slices", "resident_items",
+            "seed_rows", "keep", "tail_slices", "cluster_tiles")
+    return dict(zip(keys, list(out)))
 
 
 def launch_count() -> int:

@@ -44,10 +44,15 @@ class Bm25Index:
         self.doc_norm_np = k1 * (1 - b + b * self.doc_len_np / self.avgdl)
         self.k1_plus_1 = k1 + 1
         self.indptr_np, self.post_doc_np, self.post_tf_np = indptr, post_doc, post_tf
+        # query-independent factor of every posting, evaluated with numpy in the reference's order:
+        # tf * (k1 + 1) / (tf + k1 * (1 - b + b * dl / avgdl))
+        tf64 = post_tf.astype(np.int64)
+        self.post_val_np = tf64 * (k1 + 1) / (tf64 + self.doc_norm_np[post_doc])
         self.device = torch.device(device)
         self.indptr = torch.from_numpy(indptr.astype(np.int64)).to(self.device)
         self.post_doc = torch.from_numpy(post_doc.astype(np.int32)).to(self.device)
         self.post_tf = torch.from_numpy(post_tf.astype(np.int32)).to(self.device)
+        self.post_val = torch.from_numpy(self.post_val_np).to(self.device)
         self.idf = torch.from_numpy(idf).to(self.device)
         self.doc_norm = torch.from_numpy(self.doc_norm_np).to(self.device)
 

@@ -12,7 +12,8 @@
 //  * bm25_range_kernel (the top-k path): a CTA owns (query, range of 24 576 consecutive docs) and
 //    keeps that range's fp64 accumulators in SHARED memory (192 KB).  Posting lists are sorted by
 //    doc, so the range's postings of a term are one contiguous span found by binary search; they are
-//    streamed once (coalesced 4-byte loads of doc and tf), the read-modify-write stays on chip, and
+//    streamed once (coalesced 4-byte loads of doc and the
+//    per-posting factor), the read-modify-write stays on chip, and
 //    the range's top-k is selected straight out of shared memory.  A small merge kernel combines
 //    the per-range candidates.  HBM/L2 traffic per query = its postings (8 B each) + one 8-byte
 //    doc-norm gather per posting - the algorithmic minimum.
@@ -194,7 +195,8 @@ __device__ __forceinline__ void block_topk_f64(const double* acc, int n, int kk,
 // ---- dense-accumulator schedule ------------------------------------------------------------------
 __global__ void __launch_bounds__(bm25::THREADS)
 bm25_score_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
-                  const int32_t* __restrict__ post_tf, const double* __restrict__ idf,
+                  const int32_t* __restrict__ post_tf, const double* __restrict__ post_val,
+                  const double* __restrict__ idf,
                   const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
                   const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int q_base,
                   double* __restrict__ acc_all) {
@@ -210,7 +212,8 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
       const double w = idf[term];
       for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const int d = post_doc[i];
-        acc[d] = __dadd_rn(acc[d], bm25_term(w, (double)post_tf[i], k1p1, doc_norm[d]));
+        const double c = post_val ? __dmul_rn(w, post_val[i]) : bm25_term(w, (double)post_tf[i], k1p1, doc_norm[d]);
+        acc[d] = __dadd_rn(acc[d], c);
       }
     }
     __syncthreads();   // orders this term's accumulator updates before the next term's
@@ -232,11 +235,30 @@ bm25_topk_kernel(const double* __restrict__ acc_all, int64_t n_docs, int k, int 
   }
 }
 
+// Warp-cooperative lower bound: first index in [lo,hi) whose value is >= key (hi if none).  Every
+// round probes 32 evenly spaced entries at once, so the dependent-load chain is log33(n) long.
+__device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ p, int64_t lo, int64_t hi, int64_t key) {
+  const int lane = threadIdx.x & 31;
+  while (hi - lo > 32) {
+    const int64_t step = (hi - lo + 32) / 33;
+    const int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
+    const bool lt = idx < hi && (int64_t)p[idx] < key;
+    const int c = __popc(__ballot_sync(FULL, lt));            // probes are monotone: the first c are < key
+    const int64_t nhi = lo + (int64_t)(c + 1) * step - 1;
+    if (c < 32 && nhi < hi) hi = nhi;                         // probe c is >= key: the answer is at or before it
+    lo += (int64_t)c * step;                                  // probe c-1 is < key: the answer is after it
+  }
+  const int64_t idx = lo + lane;
+  const bool lt = idx < hi && (int64_t)p[idx] < key;
+  return lo + __popc(__ballot_sync(FULL, lt));
+}
+
 // ---- shared-memory range schedule ----------------------------------------------------------------
 // grid = (n_ranges, nq).  cand_ord/cand_id: [nq, n_ranges, k] per-range winners (0 / 0xFFFFFFFF pad).
 __global__ void __launch_bounds__(bm25::THREADS, 1)
 bm25_range_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
-                  const int32_t* __restrict__ post_tf, const double* __restrict__ idf,
+                  const int32_t* __restrict__ post_tf, const double* __restrict__ post_val,
+                  const double* __restrict__ idf,
                   const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
                   const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int k,
                   uint64_t* __restrict__ cand_ord, uint32_t* __restrict__ cand_id) {
@@ -249,33 +271,42 @@ bm25_range_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
   const int nd = (int)((n_docs - d0) < bm25::RANGE ? (n_docs - d0) : bm25::RANGE);
   for (int i = threadIdx.x; i < nd; i += blockDim.x) racc[i] = 0.0;
   const int len = q_len[q] < tmax ? q_len[q] : tmax;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int tb = 0; tb < len; tb += 32) {
-    // the posting span of each of (up to) 32 terms that falls into this doc range
-    if (threadIdx.x < 32) {
-      const int t = tb + threadIdx.x;
-      int64_t a = 0, b = 0; double w = 0.0;
-      if (t < len) {
-        const int term = q_terms[(size_t)q * tmax + t];
-        if (term >= 0) {
-          const int64_t lo = indptr[term], hi = indptr[term + 1];
-          int64_t l = lo, h = hi;                  // lower_bound(d0)
-          while (l < h) { const int64_t m = (l + h) >> 1; if (post_doc[m] < d0) l = m + 1; else h = m; }
-          a = l; h = hi;                           // lower_bound(d0 + nd)
-          while (l < h) { const int64_t m = (l + h) >> 1; if (post_doc[m] < d0 + nd) l = m + 1; else h = m; }
-          b = l; w = idf[term];
-        }
+    // the posting span of each of (up to) 32 terms that falls into this doc range: one warp per
+    // (term, bound), 32-ary search (4 dependent loads for a 1M-entry list instead of 20)
+    const int nt = len - tb < 32 ? len - tb : 32;
+    for (int p = warp; p < 2 * nt; p += nwarps) {
+      const int t = p >> 1, hi_bound = p & 1;
+      const int term = q_terms[(size_t)q * tmax + tb + t];
+      int64_t r = 0;
+      if (term >= 0) r = warp_lower_bound(post_doc, indptr[term], indptr[term + 1], hi_bound ? d0 + nd : d0);
+      if ((threadIdx.x & 31) == 0) {
+        if (hi_bound) span_hi[t] = r;
+        else { span_lo[t] = r; span_w[t] = term >= 0 ? idf[term] : 0.0; }
       }
-      span_lo[threadIdx.x] = a; span_hi[threadIdx.x] = b; span_w[threadIdx.x] = w;
     }
     __syncthreads();
-    const int nt = len - tb < 32 ? len - tb : 32;
     for (int t = 0; t < nt; ++t) {
       const int64_t a = span_lo[t], b = span_hi[t];
       const double w = span_w[t];
-      for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
-        const int d = post_doc[i];
-        const int l = (int)(d - d0);
-        racc[l] = __dadd_rn(racc[l], bm25_term(w, (double)post_tf[i], k1p1, doc_norm[d]));
+      // four postings per thread in flight: all loads first, then the shared-memory updates
+      for (int64_t i0 = a + threadIdx.x; i0 < b; i0 += 4 * (int64_t)blockDim.x) {
+        int l[4]; double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = i0 + (int64_t)u * blockDim.x;
+          l[u] = -1; v[u] = 0.0;
+          if (i < b) {
+            const int d = post_doc[i];
+            l[u] = (int)(d - d0);
+            v[u] = post_val ? post_val[i]
+                            : __ddiv_rn(__dmul_rn((double)post_tf[i], k1p1), __dadd_rn((double)post_tf[i], doc_norm[d]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (l[u] >= 0) racc[l[u]] = __dadd_rn(racc[l[u]], __dmul_rn(w, v[u]));
       }
       __syncthreads();   // term order
     }
@@ -357,7 +388,7 @@ static int bm25_check(const int64_t* indptr, const int32_t* post_doc, const int3
 }
 
 int ragarc_bm25_scores(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
-                       const double* idf, const double* doc_norm, double k1_plus_1,
+                       const double* post_val, const double* idf, const double* doc_norm, double k1_plus_1,
                        const int32_t* q_terms, const int32_t* q_len, int nq, int tmax, int64_t n_docs,
                        double* out_scores, void* stream) {
   int rc = bm25_check(indptr, post_doc, post_tf, idf, doc_norm, q_terms, q_len, nq, tmax, n_docs);
@@ -365,13 +396,13 @@ int ragarc_bm25_scores(const int64_t* indptr, const int32_t* post_doc, const int
   RA_REQUIRE(out_scores || nq == 0, "bm25_scores: null output");
   if (nq == 0) return RAGARC_OK;
   bm25_score_kernel<<<nq, bm25::THREADS, 0, (cudaStream_t)stream>>>(
-      indptr, post_doc, post_tf, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, 0, out_scores);
+      indptr, post_doc, post_tf, post_val, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, 0, out_scores);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
 
 int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
-                     const double* idf, const double* doc_norm, double k1_plus_1, const int32_t* q_terms,
+                     const double* post_val, const double* idf, const double* doc_norm, double k1_plus_1, const int32_t* q_terms,
                      const int32_t* q_len, int nq, int tmax, int64_t n_docs, int k, double* out_scores,
                      int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = bm25_check(indptr, post_doc, post_tf, idf, doc_norm, q_terms, q_len, nq, tmax, n_docs);
@@ -391,7 +422,7 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
     uint32_t* cand_id = (uint32_t*)((char*)workspace + ord_bytes);
     RA_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm25::RANGE_SMEM));
     bm25_range_kernel<<<dim3((unsigned)n_ranges, (unsigned)nq), bm25::THREADS, bm25::RANGE_SMEM, st>>>(
-        indptr, post_doc, post_tf, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, k, cand_ord, cand_id);
+        indptr, post_doc, post_tf, post_val, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, k, cand_ord, cand_id);
     RA_LAUNCH_CHECK();
     const size_t msm = (size_t)P * 12;
     if (msm > 48 * 1024)
@@ -408,7 +439,7 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
   int chunk = (int)(workspace_bytes / row < (size_t)nq ? workspace_bytes / row : (size_t)nq);
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int c = nq - q0 < chunk ? nq - q0 : chunk;
-    bm25_score_kernel<<<c, bm25::THREADS, 0, st>>>(indptr, post_doc, post_tf, idf, doc_norm, k1_plus_1,
+    bm25_score_kernel<<<c, bm25::THREADS, 0, st>>>(indptr, post_doc, post_tf, post_val, idf, doc_norm, k1_plus_1,
                                                    q_terms, q_len, tmax, n_docs, q0, (double*)workspace);
     RA_LAUNCH_CHECK();
     bm25_topk_kernel<<<c, bm25::THREADS, 0, st>>>((const double*)workspace, n_docs, k, q0, out_scores, out_ids);

@@ -44,6 +44,10 @@ static int cap_for_k(int k) {
   return 0;
 }
 
+#ifndef RAGARC_DEFAULT_TC_CL
+#define RAGARC_DEFAULT_TC_CL 1
+#endif
+
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* pl, int* path_out) {
   RA_REQUIRE(n >= 0 && d > 0 && nq >= 0 && k > 0, "dense: bad shape n=%lld d=%d nq=%d k=%d",
              (long long)n, d, nq, k);
@@ -70,38 +74,77 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   pl->rows_per_item = tc ? 128 * cg : 64;
   pl->tile_n = tc ? 256 : 64;
   pl->MB = (int)ceil_div(nq > 0 ? nq : 1, pl->rows_per_item);
+  // pairs per cluster that share each corpus tile through TMA multicast (needs that many query
+  // blocks); RAGARC_TC_CL=1|2|4 forces a variant
+  int cl = 1;
+  if (tc && cg == 2) {
+    static const char* envc = getenv("RAGARC_TC_CL");
+    const int want = envc ? atoi(envc) : RAGARC_DEFAULT_TC_CL;
+    if (want >= 4 && pl->MB % 4 == 0) cl = 4;
+    else if (want >= 2 && pl->MB % 2 == 0) cl = 2;
+  }
+  pl->cl = cl;
   pl->tiles = ceil_div(n > 0 ? n : 1, pl->tile_n);
   pl->cap = cap;
   // Slice count: work items (MB x S) should fill the persistent workers (SMs, or SM pairs for
   // cta_group::2) in whole waves - two waves when the merge capacity allows it (the second item of
   // a worker starts with the thresholds the first wave published), else one.  A ragged last wave
   // costs a full item time (measured: 163 items on 148 SMs ran 1.3x slower than 148).
-  const int64_t units = tc ? sm_count() / cg : (int64_t)sm_count() * 2;
-  // the merge kernel holds S*keep candidate keys in shared memory: 8192 normally, 16384 when that is
-  // what it takes to give every worker a slice (small batches: the merge grid is tiny then anyway)
   int64_t merge_cap = 8192;
-  if ((units / pl->MB) * (int64_t)k > merge_cap) merge_cap = 16384;
-  int64_t smax = merge_cap / k;
-  if (smax > 1024) smax = 1024;
-  if (smax > pl->tiles) smax = pl->tiles;
-  if (smax < 1) smax = 1;
   int64_t S = 0;
-  double best_eff = -1.0;
-  for (int waves = 2; waves >= 1; --waves) {
-    int64_t cand = waves * units / pl->MB;
-    if (cand < 1) cand = 1;
-    if (cand > smax) continue;
-    const int64_t items_c = cand * pl->MB;
-    const double eff = (double)items_c / (double)(ceil_div(items_c, units) * units);
-    if (eff > best_eff + 1e-9) { best_eff = eff; S = cand; }
+  pl->S_tail = 0;
+  pl->tiles_main = pl->tiles;
+  if (tc && cl > 1) {
+    // Multicast clusters (cl pairs) only fit where a GPC has 2*cl free SMs; the SMs left over host
+    // plain pairs.  Two concurrent launches share the corpus: the clusters take the first
+    // tiles_main tiles in S - S_tail slices, the left-over pairs the rest in S_tail slices, sized by
+    // the clusters' per-pair speed advantage so that both launches end together.
+    const int64_t clusters = dense_tc_units(cg, cl) / cl;
+    const int64_t spare = (sm_count() - clusters * cg * cl) / cg;
+    const int64_t units_all = clusters * cl + spare;
+    if ((units_all / pl->MB) * (int64_t)k > merge_cap) merge_cap = 16384;
+    int64_t smax = merge_cap / k;
+    if (smax > pl->tiles / 2) smax = pl->tiles / 2;
+    static const char* envr = getenv("RAGARC_TC_RHO");      // per-pair speed of a cluster vs a plain pair
+    const double rho = envr ? atof(envr) : (cl == 2 ? 1.09 : 1.15);
+    for (int waves = 2; waves >= 1 && S == 0; --waves) {
+      const int64_t sm = waves * clusters * cl / pl->MB, st = waves * spare / pl->MB;
+      if (sm < 1 || sm + st > smax) continue;
+      S = sm + st;
+      pl->S_tail = (int)st;
+      int64_t tm = (int64_t)((double)pl->tiles * (sm * rho) / (sm * rho + st) + 0.5);
+      if (tm > pl->tiles - st) tm = pl->tiles - st;
+      if (tm < sm) tm = sm;
+      pl->tiles_main = st > 0 ? tm : pl->tiles;
+    }
+    if (S == 0) { cl = 1; pl->cl = 1; merge_cap = 8192; }   // too few tiles / too many slices: plain pairs
   }
-  if (S == 0) S = smax;                 // cannot fill a wave within the merge capacity
-  {
-    static const char* envs = getenv("RAGARC_DENSE_S");     // experiments: force the slice count
-    if (envs && atoi(envs) > 0) S = atoi(envs);
+  if (S == 0) {
+    const int64_t units = tc ? dense_tc_units(cg, 1) : (int64_t)sm_count() * 2;
+    // the merge kernel holds S*keep candidate keys in shared memory: 8192 normally, 16384 when that is
+    // what it takes to give every worker a slice (small batches: the merge grid is tiny then anyway)
+    if ((units / pl->MB) * (int64_t)k > merge_cap) merge_cap = 16384;
+    int64_t smax = merge_cap / k;
+    if (smax > 1024) smax = 1024;
+    if (smax > pl->tiles) smax = pl->tiles;
+    if (smax < 1) smax = 1;
+    double best_eff = -1.0;
+    for (int waves = 2; waves >= 1; --waves) {
+      int64_t cand = waves * units / pl->MB;
+      if (cand < 1) cand = 1;
+      if (cand > smax) continue;
+      const int64_t items_c = cand * pl->MB;
+      const double eff = (double)items_c / (double)(ceil_div(items_c, units) * units);
+      if (eff > best_eff + 1e-9) { best_eff = eff; S = cand; }
+    }
+    if (S == 0) S = smax;                 // cannot fill a wave within the merge capacity
+    {
+      static const char* envs = getenv("RAGARC_DENSE_S");     // experiments: force the slice count
+      if (envs && atoi(envs) > 0) S = atoi(envs);
+    }
+    if (S < 1) S = 1;
+    if (S > pl->tiles) S = pl->tiles;
   }
-  if (S < 1) S = 1;
-  if (S > pl->tiles) S = pl->tiles;
   pl->S = (int)S;
   pl->keep = (int)(merge_cap / S);
   if (pl->keep < k) pl->keep = k;
@@ -120,7 +163,7 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
     if (sr / 16 >= 4 * (int64_t)k && n >= 8 * sr) {
       pl->seed_rows = (int)sr;
       int64_t st = sr / pl->tile_n;
-      int64_t ss = (sm_count() / cg) / pl->MB;
+      int64_t ss = dense_tc_units(cg, 1) / pl->MB;
       pl->seed_S = (int)(ss < 1 ? 1 : (ss > st ? st : ss));
     }
   }
@@ -255,6 +298,20 @@ size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, in
     if (plan_dense(n, d, dtype, nq, k, path, &pl, &use) == RAGARC_OK && pl.total > best) best = pl.total;
   }
   return best;
+}
+
+int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out10) {
+  int* out8 = out10;
+  RA_REQUIRE(out8 != nullptr, "dense_topk_plan: out is NULL");
+  DensePlan pl;
+  int use = 0;
+  int rc = plan_dense(n, d, dtype, nq, k, path, &pl, &use);
+  if (rc) return rc;
+  const bool tc = use == RAGARC_DENSE_TCGEN05;
+  out8[0] = use; out8[1] = pl.rows_per_item; out8[2] = pl.cl; out8[3] = pl.MB; out8[4] = pl.S;
+  out8[5] = tc ? dense_tc_units(pl.rows_per_item / 128, pl.cl) : sm_count() * 2;
+  out8[6] = pl.seed_rows; out8[7] = pl.keep; out8[8] = pl.S_tail; out8[9] = (int)pl.tiles_main;
+  return RAGARC_OK;
 }
 
 int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,

@@ -315,6 +315,9 @@ struct DensePlan {
   int keep;            // a list longer than this is pruned to k at item end (S*keep <= 8192)
   int seed_rows;       // >0: thresholds are seeded from exact scores of the first seed_rows rows
   int seed_S;          // corpus slices of the seed pass
+  int cl;              // tcgen05 pairs per cluster sharing corpus tiles by TMA multicast (1, 2 or 4)
+  int S_tail;          // cl > 1: the last S_tail slices run as plain pairs on the SMs no cluster fits on
+  int64_t tiles_main;  // cl > 1: corpus tiles covered by the first S - S_tail slices
   int x3_d;            // >0: rows are three bf16 planes [x1|x2|x3] of a d=x3_d fp32 vector (width 3*x3_d)
   size_t off_lists, off_counts, off_gthr, off_keys, off_qpad, off_seed, total;
 };
@@ -337,5 +340,6 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan
                        cudaStream_t stream);
 
 int sm_count();
+int dense_tc_units(int cg, int cl);   // persistent work-item slots (CTAs or pairs) the tcgen05 kernel keeps resident
 
 }  // namespace ragarc

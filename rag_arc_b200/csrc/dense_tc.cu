@@ -20,6 +20,7 @@
 // 16 consecutive corpus rows (see merge.cu: seed_select_kernel).
 #include <cuda.h>
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 
 namespace ragarc {
@@ -95,20 +96,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
   }
 }
+// CG=2 multicast variant: the tile lands at the same shared-memory offset in every CTA of `mask`
+// and the bytes are signalled on the leader barrier of each destination's own pair.
+__device__ __forceinline__ void tma_load_2d_mc2(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 // TMA prefetch of a tile into L2 only (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// MMA completion -> mbarrier.  CG=2: arrive on the barrier of BOTH CTAs of the pair.
+// MMA completion -> mbarrier.  CG=2: arrive on the barrier (same offset) of every CTA in `mask`.
 template <int CG>
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+__device__ __forceinline__ void tc_commit(uint64_t* bar, uint16_t mask) {
   if (CG == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   } else {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
   }
 }
 template <int CG>
@@ -149,7 +157,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct Params {
   int64_t n;       // corpus rows
   int nq, k, num_kb, MB, S;
-  int64_t tiles;
+  int64_t tiles;   // corpus tiles of THIS launch, split into S slices, starting at tile_base
+  int64_t tile_base;
+  int slice_base;  // candidate lists are indexed by (slice_base + slice, query block)
   int cap, keep;
   uint32_t idesc;
   uint64_t* lists;
@@ -163,7 +173,11 @@ struct Params {
 
 constexpr int MODE_TOPK = 0, MODE_STORE = 1;
 
-template <int MODE, int CG>
+// CL = CTA pairs per cluster (CG=2 only).  With CL > 1 the pairs of a cluster work on the same
+// corpus tiles for CL adjacent query blocks: every CTA loads 1/CL of its corpus half-tile and
+// multicasts it to the CTAs holding the same half in the other pairs, which divides the corpus
+// operand's L2->SM traffic by CL (the kernel is bound by L2 bandwidth, not by the tensor pipe).
+template <int MODE, int CG, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                 const Params p) {
@@ -181,15 +195,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256 + 4 * 256 * 4);   // [4][32][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();        // 0 = leader CTA of the pair
-  const int unit = CG == 1 ? blockIdx.x : blockIdx.x >> 1;       // persistent worker id
-  const int nunits = CG == 1 ? gridDim.x : gridDim.x >> 1;
+  static_assert(CL == 1 || CG == 2, "multicast clusters are built from CTA pairs");
+  constexpr int CSIZE = CG * CL;                                 // CTAs per cluster
+  const uint32_t crank = CSIZE == 1 ? 0u : cluster_ctarank();
+  const uint32_t rank = crank & (CG - 1);                        // 0 = leader CTA of the pair
+  const uint32_t pair = crank / CG;                              // pair inside the cluster
+  const int unit = blockIdx.x / CSIZE;                           // persistent worker (cluster) id
+  const int nunits = gridDim.x / CSIZE;
   constexpr int ROWS_ITEM = BM * CG;                             // query rows per work item
+  const int MBq = p.MB / CL;                                     // query-block groups (CL blocks each)
+  const uint16_t mask_all = (uint16_t)((1u << CSIZE) - 1);       // every CTA of the cluster
+  const uint16_t mask_pair = (uint16_t)(3u << (crank & ~1u));    // this CTA's pair
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,19 +228,21 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t items = (int64_t)p.MB * p.S;
+  const int64_t items = (int64_t)MBq * p.S;       // cluster work items: (query-block group, slice)
 
   if (warp == 0) {
     // ------------------------------ TMA producer (every CTA) ------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      constexpr int B_ROWS = C::BN_CTA / CL;       // corpus rows this CTA fetches per tile
+      const uint16_t mask_half = (uint16_t)((CL == 1 ? 0x1u : CL == 2 ? 0x5u : 0x55u) << rank);
       for (int64_t item = unit; item < items; item += nunits) {
-        const int qb = (int)(item % p.MB);
-        const int64_t s = item / p.MB;
-        const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+        const int qb = (int)(item % MBq) * CL + (int)pair;
+        const int64_t s = item / MBq;
+        const int64_t t0 = p.tile_base + s * p.tiles / p.S, t1 = p.tile_base + (s + 1) * p.tiles / p.S;
         const int q0 = qb * ROWS_ITEM + (int)rank * BM;
         for (int64_t t = t0; t < t1; ++t) {
-          const int x0 = (int)(t * BN) + (int)rank * C::BN_CTA;
+          const int x0 = (int)(t * BN) + (int)rank * C::BN_CTA + (int)pair * B_ROWS;
           // corpus rows one tile ahead are pulled into L2 now, so that the ring's refills (which
           // have ~5 stage-times to land) see L2 latency instead of HBM latency
           const bool pf = p.prefetch > 0 && (t + p.prefetch < t1);
@@ -237,7 +260,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               kx = (((0x001021 >> (4 * pair)) & 0xF) * p.kb_per_plane + kk) * BK;
             }
             tma_load_2d<CG>(a, &tmap_q, &full_bar[stage], ka, q0);
-            tma_load_2d<CG>(a + A_BYTES, &tmap_x, &full_bar[stage], kx, x0);
+            if (CL == 1) tma_load_2d<CG>(a + A_BYTES, &tmap_x, &full_bar[stage], kx, x0);
+            else tma_load_2d_mc2(a + A_BYTES + pair * (B_ROWS * BK * 2), &tmap_x, &full_bar[stage], kx, x0, mask_half);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -249,8 +273,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       uint32_t tcount = 0;
       for (int64_t item = unit; item < items; item += nunits) {
-        const int64_t s = item / p.MB;
-        const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+        const int64_t s = item / MBq;
+        const int64_t t0 = p.tile_base + s * p.tiles / p.S, t1 = p.tile_base + (s + 1) * p.tiles / p.S;
         for (int64_t t = t0; t < t1; ++t, ++tcount) {
           const uint32_t buf = tcount & 1, aphase = (tcount >> 1) & 1;
           mbar_wait(&tempty_bar[buf], aphase ^ 1);
@@ -268,10 +292,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               tc_mma<CG>(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
                          (uint32_t)((kb | k4) != 0));
             }
-            tc_commit<CG>(&empty_bar[stage]);   // frees the smem stage (in both CTAs) when the MMAs retire
+            tc_commit<CG>(&empty_bar[stage], mask_all);   // frees the smem stage (in every CTA that may write it) when the MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit<CG>(&tfull_bar[buf]);       // accumulator complete (signalled in both CTAs)
+          tc_commit<CG>(&tfull_bar[buf], mask_pair);    // accumulator complete (signalled in both CTAs of the pair)
         }
       }
     }
@@ -285,10 +309,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float* mystage = stage_all + (warp - 2) * 1024 + lane * 32;
     const int swz = lane & 7;
     uint32_t tcount = 0;
-    for (int64_t item = unit; item < items; item += nunits) {
-      const int qb = (int)(item % p.MB);
-      const int64_t s = item / p.MB;
-      const int64_t t0 = s * p.tiles / p.S, t1 = (s + 1) * p.tiles / p.S;
+    for (int64_t citem = unit; citem < items; citem += nunits) {
+      const int qb = (int)(citem % MBq) * CL + (int)pair;
+      const int64_t s = citem / MBq;
+      const int64_t item = (p.slice_base + s) * p.MB + qb;   // (slice, query block): index of the candidate lists
+      const int64_t t0 = p.tile_base + s * p.tiles / p.S, t1 = p.tile_base + (s + 1) * p.tiles / p.S;
       const int irow = (int)rank * BM + row;       // row inside the work item
       const int qrow = qb * ROWS_ITEM + irow;
       RowState st;
@@ -355,7 +380,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) {
           // the accumulator is drained: tell the MMA issuer (in the leader CTA)
-          if (rank == 0) mbar_arrive(&tempty_bar[buf]); else mbar_arrive_remote(&tempty_bar[buf], 0);
+          if (rank == 0) mbar_arrive(&tempty_bar[buf]); else mbar_arrive_remote(&tempty_bar[buf], crank & ~1u);
         }
       }
       if (MODE == MODE_TOPK) {
@@ -366,7 +391,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   tc_fence_before();
-  if (CG == 1) __syncthreads(); else cluster_sync_all();   // pair: nobody leaves while the peer still uses us
+  if (CG == 1) __syncthreads(); else cluster_sync_all();   // cluster: nobody leaves while a peer still uses us
   if (warp == 1) {
     tc_fence_after();
     if (CG == 1)
@@ -409,31 +434,86 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int
   return RAGARC_OK;
 }
 
-template <int MODE, int CG>
+// how many clusters of CG*CL CTAs the device keeps resident at once (GPC boundaries decide)
+template <int MODE, int CG, int CL>
+static int max_clusters() {
+  static int cached = 0;
+  if (cached) return cached;
+  using C = Cfg<CG>;
+  int n = sm_count() / (CG * CL);
+  if (CG * CL > 1 &&
+      cudaFuncSetAttribute(dense_tc_kernel<MODE, CG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sm_count() / (CG * CL) * (CG * CL)));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG * CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int got = 0;
+    if (cudaOccupancyMaxActiveClusters(&got, dense_tc_kernel<MODE, CG, CL>, &cfg) == cudaSuccess && got > 0 && got < n) n = got;
+    (void)cudaGetLastError();
+  }
+  cached = n > 0 ? n : 1;
+  return cached;
+}
+
+template <int MODE, int CG, int CL>
 static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, cudaStream_t stream) {
   using C = Cfg<CG>;
-  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const int64_t items = (int64_t)p.MB * p.S;
-  const int max_units = sm_count() / CG;
+  RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE, CG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  RA_REQUIRE(p.MB % CL == 0, "dense tcgen05: query blocks not divisible by the cluster's pair count");
+  const int64_t items = (int64_t)(p.MB / CL) * p.S;
+  const int max_units = max_clusters<MODE, CG, CL>();
   const int units = (int)(items < max_units ? items : max_units);
+  constexpr int CG_ = CG * CL;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.gridDim = dim3((unsigned)(units * CG_));
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG_;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RA_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<MODE, CG>, mq, mx, p));
+  RA_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<MODE, CG, CL>, mq, mx, p));
   count_launch();
   return RAGARC_OK;
 }
 
+// side stream for the launch that runs concurrently with the multicast clusters (one per device)
+struct Side { cudaStream_t stream; cudaEvent_t fork, join; };
+static Side* get_side() {
+  static std::mutex mu;
+  static Side sides[64];
+  static bool made[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!made[dev]) {
+    Side s{};
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    sides[dev] = s;
+    made[dev] = true;
+  }
+  return &sides[dev];
+}
+
 }  // namespace tc
+
+int dense_tc_units(int cg, int cl) {
+  using namespace tc;
+  if (cg == 1) return max_clusters<MODE_TOPK, 1, 1>();
+  if (cl == 4) return max_clusters<MODE_TOPK, 2, 4>() * 4;
+  if (cl == 2) return max_clusters<MODE_TOPK, 2, 2>() * 2;
+  return max_clusters<MODE_TOPK, 2, 1>();
+}
 
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries) {
   if (dtype != RAGARC_BF16 && dtype != RAGARC_F16) return false;
@@ -449,7 +529,9 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
              "dense tcgen05: needs bf16/fp16, d %% 8 == 0 and 16-byte aligned base pointers");
   const int cg = pl.rows_per_item / BM;          // 1 or 2 (chosen by the planner)
-  RA_REQUIRE(cg == 1 || cg == 2, "dense tcgen05: bad plan");
+  const int cl = pl.cl;                          // pairs per cluster: 1, 2 or 4 (cg == 2 only)
+  RA_REQUIRE((cg == 1 && cl == 1) || (cg == 2 && (cl == 1 || cl == 2 || cl == 4) && pl.MB % cl == 0),
+             "dense tcgen05: bad plan");
   // Queries are staged into a buffer padded with zero rows up to a whole number of work-item rows,
   // so that every query-tile TMA load is fully in bounds (out-of-bounds fill was measured slower for
   // tiny batches: 1 query in a 128-row box).
@@ -464,7 +546,7 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   CUtensorMap mq, mx;
   int rc = make_map(&mq, qsrc, q_rows, d, dtype, BM);
   if (rc) return rc;
-  rc = make_map(&mx, corpus, n, d, dtype, BN / cg);
+  rc = make_map(&mx, corpus, n, d, dtype, BN / cg / cl);
   if (rc) return rc;
   Params p;
   p.n = n; p.nq = nq; p.k = k; p.MB = pl.MB; p.S = pl.S;
@@ -472,7 +554,7 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   // product is the sum of the six largest plane-pair products, i.e. six passes over x3_d
   p.kb_per_plane = pl.x3_d > 0 ? pl.x3_d / BK : 0;
   p.num_kb = pl.x3_d > 0 ? 6 * p.kb_per_plane : (d + BK - 1) / BK;
-  p.tiles = pl.tiles; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
+  p.tiles = pl.tiles; p.tile_base = 0; p.slice_base = 0; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
   p.seed_out = nullptr; p.seed_ld = 0;
   {
     static const char* env = getenv("RAGARC_TC_PREFETCH");
@@ -493,13 +575,44 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
     ps.S = pl.seed_S;
     ps.seed_out = seed_scores;
     ps.seed_ld = pl.seed_rows / 16;
-    rc = cg == 1 ? launch_one<MODE_STORE, 1>(mq, mxs, ps, stream) : launch_one<MODE_STORE, 2>(mq, mxs, ps, stream);
+    rc = cg == 1 ? launch_one<MODE_STORE, 1, 1>(mq, mxs, ps, stream) : launch_one<MODE_STORE, 2, 1>(mq, mxs, ps, stream);
     if (rc) return rc;
     rc = launch_seed_select(seed_scores, nq, pl.seed_rows / 16, k, gthr, stream);
     if (rc) return rc;
   }
   if (after_seed) RA_CUDA(cudaEventRecord(after_seed, stream));
-  return cg == 1 ? launch_one<MODE_TOPK, 1>(mq, mx, p, stream) : launch_one<MODE_TOPK, 2>(mq, mx, p, stream);
+  if (cg == 1) return launch_one<MODE_TOPK, 1, 1>(mq, mx, p, stream);
+  if (cl == 1) return launch_one<MODE_TOPK, 2, 1>(mq, mx, p, stream);
+  // Multicast clusters on the caller's stream and - concurrently, on the SMs no cluster fits on -
+  // plain pairs on a side stream (forked and joined with events, so the call stays stream-ordered
+  // and capturable).  Programmatic dependent launch in one stream was tried instead and did not
+  // overlap the two launches (measured: they ran back to back).
+  p.S = pl.S - pl.S_tail;
+  p.tiles = pl.tiles_main;
+  Side* side = nullptr;
+  if (pl.S_tail > 0) {
+    side = get_side();
+    RA_REQUIRE(side != nullptr, "dense tcgen05: cannot create the side stream");
+    RA_CUDA(cudaEventRecord(side->fork, stream));
+    RA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  rc = cl == 4 ? launch_one<MODE_TOPK, 2, 4>(mq, mx, p, stream) : launch_one<MODE_TOPK, 2, 2>(mq, mx, p, stream);
+  if (rc) return rc;
+  if (side) {
+    CUtensorMap mxt;
+    rc = make_map(&mxt, corpus, n, d, dtype, BN / cg);
+    if (rc) return rc;
+    Params pt = p;
+    pt.S = pl.S_tail;
+    pt.tiles = pl.tiles - pl.tiles_main;
+    pt.tile_base = pl.tiles_main;
+    pt.slice_base = pl.S - pl.S_tail;
+    rc = launch_one<MODE_TOPK, 2, 1>(mq, mxt, pt, side->stream);
+    if (rc) return rc;
+    RA_CUDA(cudaEventRecord(side->join, side->stream));
+    RA_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
+  }
+  return RAGARC_OK;
 }
 
 }  // namespace ragarc

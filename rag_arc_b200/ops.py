@@ -196,8 +196,14 @@ def merge_topk_keys_p2p(ptr_table: torch.Tensor, nq: int, k_in: int, k_out: int,
     return scores, ids
 
 
-def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
-    """index: object with device tensors indptr/post_doc/post_tf/idf/doc_norm and k1_plus_1, n_docs."""
+def _post_val_ptr(index, use_post_val: bool) -> int:
+    pv = getattr(index, "post_val", None) if use_post_val else None
+    return pv.data_ptr() if pv is not None else 0
+
+
+def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int, use_post_val: bool = True):
+    """index: object with device tensors indptr/post_doc/post_tf/idf/doc_norm (and optionally the
+    precomputed per-posting factor post_val) and k1_plus_1, n_docs."""
     _cuda(q_terms, "q_terms"); _cuda(q_len, "q_len")
     nq, tmax = q_terms.shape
     dev = q_terms.device
@@ -206,7 +212,7 @@ def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
     ws = _workspace(dev, int(N.lib.ragarc_bm25_workspace_bytes(index.n_docs, max(nq, 1))), "bm25")
     with torch.cuda.device(dev):
         N.check(N.lib.ragarc_bm25_topk(index.indptr.data_ptr(), index.post_doc.data_ptr(),
-                                       index.post_tf.data_ptr(), index.idf.data_ptr(),
+                                       index.post_tf.data_ptr(), _post_val_ptr(index, use_post_val), index.idf.data_ptr(),
                                        index.doc_norm.data_ptr(), float(index.k1_plus_1),
                                        q_terms.data_ptr(), q_len.data_ptr(), nq, tmax, index.n_docs, k,
                                        scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -214,14 +220,14 @@ def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
     return scores, ids
 
 
-def bm25_scores(index, q_terms: torch.Tensor, q_len: torch.Tensor) -> torch.Tensor:
+def bm25_scores(index, q_terms: torch.Tensor, q_len: torch.Tensor, use_post_val: bool = True) -> torch.Tensor:
     _cuda(q_terms, "q_terms"); _cuda(q_len, "q_len")
     nq, tmax = q_terms.shape
     dev = q_terms.device
     out = torch.empty((nq, index.n_docs), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         N.check(N.lib.ragarc_bm25_scores(index.indptr.data_ptr(), index.post_doc.data_ptr(),
-                                         index.post_tf.data_ptr(), index.idf.data_ptr(),
+                                         index.post_tf.data_ptr(), _post_val_ptr(index, use_post_val), index.idf.data_ptr(),
                                          index.doc_norm.data_ptr(), float(index.k1_plus_1),
                                          q_terms.data_ptr(), q_len.data_ptr(), nq, tmax, index.n_docs,
                                          out.data_ptr(), _stream_ptr(dev)), "bm25_scores")

@@ -61,6 +61,13 @@ def test_bm25_c2_shape_bit_exact_against_csr_oracle(dev):
         _tie_aware_ids(ids[i], want, 50)
         assert np.array_equal(sc[i].view(np.uint64), want[ids[i]].view(np.uint64)), f"q{i}"
         assert ids[i].tolist() == obm25.stable_topk(want, 50).tolist()
+    # the in-kernel evaluation of the per-posting factor (no precomputed table) is bit-identical
+    sc2, ids2 = ops.bm25_topk(idx, qt, ql, 50, use_post_val=False)
+    assert np.array_equal(sc2.cpu().numpy().view(np.uint64), sc.view(np.uint64))
+    assert np.array_equal(ids2.cpu().numpy(), ids)
+    full_a = ops.bm25_scores(idx, qt[:8].contiguous(), ql[:8].contiguous())
+    full_b = ops.bm25_scores(idx, qt[:8].contiguous(), ql[:8].contiguous(), use_post_val=False)
+    assert torch.equal(full_a.view(torch.int64), full_b.view(torch.int64))
 
 
 def test_bm25_fewer_matches_than_k_fills_with_zero_score_docs(dev):

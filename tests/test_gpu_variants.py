@@ -17,7 +17,7 @@ from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
 dev = torch.device("cuda:0")
 x = synth.dense_corpus_cuda(300_000, 256, torch.bfloat16, dev, seed=5)
 out = []
-for nq, k in ((300, 100), (40, 10), (1, 5)):
+for nq, k in ((300, 100), (1000, 50), (40, 10), (1, 5)):
     q, _ = synth.dense_queries_cuda(x, nq, seed=6)
     s, i = ops.dense_topk(x, q, k)
     out.append(i.cpu().numpy()); out.append(s.cpu().numpy())
@@ -43,6 +43,7 @@ def test_forced_variants_agree_bitwise(tmp_path):
     import numpy as np
     base = _run(tmp_path, "default", {})
     for name, env in (("cg1", {"RAGARC_TC_CG": "1"}), ("cg2", {"RAGARC_TC_CG": "2"}),
+                      ("cl2", {"RAGARC_TC_CL": "2"}), ("cl4", {"RAGARC_TC_CL": "4"}),
                       ("slices", {"RAGARC_DENSE_S": "5"}), ("bm25dense", {"RAGARC_BM25_DENSE": "1"})):
         got = _run(tmp_path, name, env)
         for a, b in zip(base, got):
