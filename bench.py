@@ -372,6 +372,30 @@ def run_ours(args):
             e2e_api = ("B200VectorStore.pipeline(nq,k).submit(pinned host fp32 queries)/result() -> pinned host "
                        "scores+ids; double-buffered, wall-clock timed")
     e2e_qps = args.steps * BATCH / (e2e_ms * 1e-3)
+    # (c) the plain C ABI with HOST buffers and no torch on the path: ragarc_index_search on a
+    # library-owned index (pageable numpy arrays in and out, synchronous call); reported beside (a)/(b)
+    cabi_ms = None
+    if world == 1 and n_local * DIM * 2 < 20e9:
+        import ctypes
+        h = ctypes.c_void_p()
+        N.check(N.lib.ragarc_index_create(DIM, N.BF16 if DTYPE == "bfloat16" else N.F16, N.METRIC_COSINE,
+                                          ctypes.byref(h)), "index_create")
+        N.check(N.lib.ragarc_index_reserve(h, n_local, None), "index_reserve")
+        for a in range(0, n_local, 131072):
+            chunk = store.index.rows[a:min(n_local, a + 131072)].float()
+            N.check(N.lib.ragarc_index_add(h, chunk.data_ptr(), chunk.shape[0], 0, None), "index_add")
+        torch.cuda.synchronize()
+        q_np = q_host.numpy()
+        D = np.empty((BATCH, TOPK), np.float32); I = np.empty((BATCH, TOPK), np.int64)
+        n_cabi = max(5, min(args.steps, 50))
+        for it in range(3 + n_cabi):
+            if it == 3:
+                t0 = time.perf_counter()
+            N.check(N.lib.ragarc_index_search(h, q_np.ctypes.data, BATCH, TOPK, D.ctypes.data, I.ctypes.data, 1, None),
+                    "index_search")
+        cabi_ms = (time.perf_counter() - t0) * 1e3 / n_cabi
+        assert (I[:, 0] == res_ids_host[:, 0].numpy()).all()
+        N.lib.ragarc_index_free(h)
 
     # ---- roofline of the scoring kernel (this rank's launch) ---------------------------------------
     flops = 2.0 * BATCH * n_local * DIM
@@ -437,7 +461,8 @@ def run_ours(args):
                    "l2_policy": f"inputs larger than L2 ({n_local * DIM * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIM * 4,
                 "d2h_bytes_per_step": BATCH * TOPK * 12, "ms_per_step": e2e_ms / args.steps,
-                "sync_ms_per_step": e2e_sync_ms / args.steps, "api": e2e_api},
+                "sync_ms_per_step": e2e_sync_ms / args.steps, "api": e2e_api,
+                "cabi_host_call_ms": cabi_ms},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

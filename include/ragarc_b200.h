@@ -7,9 +7,11 @@
  * INTEGRATION.md for the ctypes stub).
  *
  * Conventions
- *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
- *     buffers, the library keeps no state between calls (no handles, no globals except the
- *     thread-local error string);
+ *   - every pointer is a DEVICE pointer unless the name ends in _host (or a flag says so); the
+ *     caller owns all buffers and the compute entry points keep no state between calls (no
+ *     globals except the thread-local error string).  The one object the library owns is the
+ *     optional ragarc_index_t (ragarc_index_*), a flat index that holds its row matrix,
+ *     workspace and staging buffers itself for hosts that do not want to manage device memory;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
  *     asynchronous on that stream, re-entrant, and may be made from any host thread
  *     (core/retrieval/base.py:82-96 runs retrievers from a thread pool);
@@ -43,6 +45,9 @@ enum { RAGARC_F32 = 0, RAGARC_BF16 = 1, RAGARC_F16 = 2 };
 
 /* pooling modes (sentence-transformers Pooling module) */
 enum { RAGARC_POOL_MEAN = 0, RAGARC_POOL_CLS = 1, RAGARC_POOL_LAST = 2 };
+
+/* similarity of a ragarc_index_t: raw inner product, or cosine (rows and queries L2-normalised) */
+enum { RAGARC_METRIC_IP = 0, RAGARC_METRIC_COSINE = 1 };
 
 /* which dense scoring kernel ran / should run */
 enum { RAGARC_DENSE_AUTO = 0, RAGARC_DENSE_SIMT = 1, RAGARC_DENSE_TCGEN05 = 2 };
@@ -91,6 +96,38 @@ int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path,
 int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                       int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
                       size_t workspace_bytes, int path, int* path_used_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flat exact index object.   Replaces faiss.IndexFlatIP as FaissVectorStore drives it:
+ *   faiss.IndexFlatIP(d)            VectorStore_Faiss.py:114-115,125-126,135-136  -> ragarc_index_create
+ *   normalize_L2 + index.add        :169-178,202                                   -> ragarc_index_add
+ *   normalize_L2 + index.search     :258-263                                       -> ragarc_index_search
+ *   index.ntotal                    :201,262                                       -> ragarc_index_ntotal
+ *   index.remove_ids + renumbering  :385-419                                       -> ragarc_index_remove
+ * The index lives on the CUDA device that is current at creation.  Rows are given as fp32 (what the
+ * reference hands to FAISS), L2-normalised on add when metric == RAGARC_METRIC_COSINE (zero rows
+ * untouched) and stored as `dtype`; queries are fp32 and get the same treatment.  `*_on_host` != 0
+ * means the fp32 / result pointers are plain host memory: the call stages them through the device
+ * itself and returns when the host buffers are reusable / filled; otherwise they are device
+ * pointers and the call is asynchronous on `stream`.  Calls on one index are serialised (host
+ * mutex + GPU ordering across streams); different indexes are independent.
+ * Search results follow ragarc_dense_topk (descending score, ties by ascending row, -1 padding).
+ */
+typedef struct ragarc_index ragarc_index_t;
+int ragarc_index_create(int d, int dtype, int metric, ragarc_index_t** out);
+int ragarc_index_free(ragarc_index_t* index);
+int ragarc_index_reserve(ragarc_index_t* index, int64_t capacity, void* stream);
+int ragarc_index_add(ragarc_index_t* index, const float* rows, int64_t n, int rows_on_host, void* stream);
+int ragarc_index_search(ragarc_index_t* index, const float* queries, int nq, int k, float* out_scores,
+                        int64_t* out_ids, int buffers_on_host, void* stream);
+/* drops the given rows (host array, any order, duplicates allowed); survivors keep their order and
+ * are renumbered densely, exactly as faiss remove_ids does */
+int ragarc_index_remove(ragarc_index_t* index, const int64_t* rows_host, int64_t n_remove, void* stream);
+int64_t ragarc_index_ntotal(const ragarc_index_t* index);
+int ragarc_index_dim(const ragarc_index_t* index);
+/* device pointer to the [ntotal, d] row matrix in the storage dtype (valid until the next add /
+ * reserve / remove), e.g. as the candidate source of ragarc_mmr_select */
+const void* ragarc_index_rows(const ragarc_index_t* index);
 
 /* fp32-accurate search on the tensor cores ("bf16x3").  An fp32 vector v is stored as three bf16
  * planes v1+v2+v3 (v1 = bf16(v), v2 = bf16(v-v1), v3 = bf16(v-v1-v2); exact to 2^-24 relative), a
@@ -152,6 +189,13 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
                      int64_t n_docs, int k, double* out_scores /* [nq,k] */,
                      int64_t* out_ids /* [nq,k] */, void* workspace, size_t workspace_bytes,
                      void* stream);
+
+/* Doc-range sharded BM25 (multi-GPU): every shard scores its own documents with the GLOBAL idf and
+ * average length (the reference computes both over the whole corpus, bm25.py:218) and reports global
+ * doc ids; this merges the per-shard results scores/ids [n_lists, nq, k_in] (ids -1 = padding) into
+ * the global top-k_out of each query with the same order rule (n_lists*k_in <= 8192). */
+int ragarc_bm25_merge_topk(const double* scores, const int64_t* ids, int n_lists, int nq, int k_in,
+                           int k_out, double* out_scores, int64_t* out_ids, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Reciprocal-rank fusion.   Replaces RRFusion.fuse at core/utils/Fusion.py:45-76 for a batch.

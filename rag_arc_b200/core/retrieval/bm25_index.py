@@ -48,13 +48,42 @@ class Bm25Index:
         # tf * (k1 + 1) / (tf + k1 * (1 - b + b * dl / avgdl))
         tf64 = post_tf.astype(np.int64)
         self.post_val_np = tf64 * (k1 + 1) / (tf64 + self.doc_norm_np[post_doc])
+        self.id_base = 0
+        self.device = None
+        if device is not None:
+            self._upload(device)
+
+    def _upload(self, device):
         self.device = torch.device(device)
-        self.indptr = torch.from_numpy(indptr.astype(np.int64)).to(self.device)
-        self.post_doc = torch.from_numpy(post_doc.astype(np.int32)).to(self.device)
-        self.post_tf = torch.from_numpy(post_tf.astype(np.int32)).to(self.device)
+        self.indptr = torch.from_numpy(self.indptr_np.astype(np.int64)).to(self.device)
+        self.post_doc = torch.from_numpy(self.post_doc_np.astype(np.int32)).to(self.device)
+        self.post_tf = torch.from_numpy(self.post_tf_np.astype(np.int32)).to(self.device)
         self.post_val = torch.from_numpy(self.post_val_np).to(self.device)
-        self.idf = torch.from_numpy(idf).to(self.device)
+        self.idf = torch.from_numpy(self.idf_np).to(self.device)
         self.doc_norm = torch.from_numpy(self.doc_norm_np).to(self.device)
+
+    def shard(self, lo: int, hi: int, device) -> "Bm25Index":
+        """The index of documents ``[lo, hi)`` for doc-range sharded (multi-GPU) search: postings and
+        length normalisers of those documents only, local doc ids ``doc - lo`` (``id_base = lo`` maps
+        results back), but the GLOBAL idf table, average length and vocabulary - the reference
+        derives all three from the whole corpus (bm25.py:218), so every shard must use the same
+        values for the merged result to equal the single-index one bit for bit."""
+        import copy
+        sh = copy.copy(self)
+        keep = (self.post_doc_np >= lo) & (self.post_doc_np < hi)
+        V = len(self.indptr_np) - 1
+        term_of = np.repeat(np.arange(V, dtype=np.int64), np.diff(self.indptr_np))
+        sh.indptr_np = np.zeros(V + 1, np.int64)
+        np.cumsum(np.bincount(term_of[keep], minlength=V), out=sh.indptr_np[1:])
+        sh.post_doc_np = (self.post_doc_np[keep] - lo).astype(np.int32)
+        sh.post_tf_np = self.post_tf_np[keep]
+        sh.post_val_np = self.post_val_np[keep]
+        sh.doc_len_np = self.doc_len_np[lo:hi]
+        sh.doc_norm_np = self.doc_norm_np[lo:hi]
+        sh.n_docs = int(hi - lo)
+        sh.id_base = int(lo)
+        sh._upload(device)
+        return sh
 
     # -- construction --------------------------------------------------------------------------
     @classmethod

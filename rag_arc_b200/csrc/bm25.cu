@@ -321,17 +321,8 @@ bm25_range_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
   }
 }
 
-// one CTA per query: sort the n_ranges*k candidates by (score desc, id asc), emit the first k
-__global__ void bm25_merge_kernel(const uint64_t* __restrict__ cand_ord, const uint32_t* __restrict__ cand_id,
-                                  int n_ranges, int k, int64_t n_docs, int P, double* __restrict__ out_scores,
-                                  int64_t* __restrict__ out_ids) {
-  extern __shared__ uint64_t mo[];                  // [P] ords then [P] ids (uint32)
-  uint32_t* mi = (uint32_t*)(mo + P);
-  const int q = blockIdx.x, total = n_ranges * k;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    mo[i] = i < total ? cand_ord[(size_t)q * total + i] : 0ull;
-    mi[i] = i < total ? cand_id[(size_t)q * total + i] : 0xFFFFFFFFu;
-  }
+// bitonic sort of P (power of two) candidates in shared memory by (score desc, id asc); all threads
+__device__ __forceinline__ void sort_candidates(uint64_t* mo, uint32_t* mi, int P) {
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
@@ -346,11 +337,51 @@ __global__ void bm25_merge_kernel(const uint64_t* __restrict__ cand_ord, const u
     }
   }
   __syncthreads();
+}
+
+// one CTA per query: sort the n_ranges*k candidates by (score desc, id asc), emit the first k
+__global__ void bm25_merge_kernel(const uint64_t* __restrict__ cand_ord, const uint32_t* __restrict__ cand_id,
+                                  int n_ranges, int k, int64_t n_docs, int P, double* __restrict__ out_scores,
+                                  int64_t* __restrict__ out_ids) {
+  extern __shared__ uint64_t mo[];                  // [P] ords then [P] ids (uint32)
+  uint32_t* mi = (uint32_t*)(mo + P);
+  const int q = blockIdx.x, total = n_ranges * k;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    mo[i] = i < total ? cand_ord[(size_t)q * total + i] : 0ull;
+    mi[i] = i < total ? cand_id[(size_t)q * total + i] : 0xFFFFFFFFu;
+  }
+  sort_candidates(mo, mi, P);
   const int kk = (int64_t)k < n_docs ? k : (int)n_docs;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const bool ok = j < kk && mi[j] != 0xFFFFFFFFu;
     out_scores[(size_t)q * k + j] = ok ? ord_to_f64(mo[j]) : -INFINITY;
     out_ids[(size_t)q * k + j] = ok ? (int64_t)mi[j] : -1;
+  }
+}
+
+// Doc-range sharded BM25: merge the per-shard results [n_lists, nq, k_in] (fp64 scores, global doc
+// ids, -1 = padding) of each query into its global top-k_out, same order rule.
+__global__ void bm25_merge_shards_kernel(const double* __restrict__ scores, const int64_t* __restrict__ ids,
+                                         int n_lists, int nq, int k_in, int k_out, int P,
+                                         double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  extern __shared__ uint64_t mo[];
+  uint32_t* mi = (uint32_t*)(mo + P);
+  const int q = blockIdx.x, total = n_lists * k_in;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    uint64_t o = 0ull; uint32_t id = 0xFFFFFFFFu;
+    if (i < total) {
+      const int g = i / k_in, j = i - g * k_in;
+      const size_t src = ((size_t)g * nq + q) * k_in + j;
+      const int64_t d = ids[src];
+      if (d >= 0) { o = f64_to_ord(scores[src]); id = (uint32_t)d; }
+    }
+    mo[i] = o; mi[i] = id;
+  }
+  sort_candidates(mo, mi, P);
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    const bool ok = j < P && mi[j] != 0xFFFFFFFFu;
+    out_scores[(size_t)q * k_out + j] = ok ? ord_to_f64(mo[j]) : -INFINITY;
+    out_ids[(size_t)q * k_out + j] = ok ? (int64_t)mi[j] : -1;
   }
 }
 
@@ -445,6 +476,26 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
     bm25_topk_kernel<<<c, bm25::THREADS, 0, st>>>((const double*)workspace, n_docs, k, q0, out_scores, out_ids);
     RA_LAUNCH_CHECK();
   }
+  return RAGARC_OK;
+}
+
+int ragarc_bm25_merge_topk(const double* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out,
+                           double* out_scores, int64_t* out_ids, void* stream) {
+  RA_REQUIRE(n_lists >= 1 && nq >= 0 && k_in >= 1 && k_out >= 1, "bm25_merge_topk: bad shape");
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(scores && ids && out_scores && out_ids, "bm25_merge_topk: null pointer");
+  const int64_t total = (int64_t)n_lists * k_in;
+  RA_REQUIRE(total <= 8192, "bm25_merge_topk: n_lists*k_in=%lld > 8192", (long long)total);
+  int P = 32;
+  while (P < total) P <<= 1;
+  const size_t msm = (size_t)P * 12;
+  if (msm > 48 * 1024)
+    RA_CUDA(cudaFuncSetAttribute(bm25_merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+  int threads = P / 2 < 1024 ? P / 2 : 1024;
+  if (threads < 32) threads = 32;
+  bm25_merge_shards_kernel<<<nq, threads, msm, (cudaStream_t)stream>>>(scores, ids, n_lists, nq, k_in, k_out, P,
+                                                                      out_scores, out_ids);
+  RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
 

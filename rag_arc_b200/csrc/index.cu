@@ -1,0 +1,276 @@
+// ragarc_index_*: a flat exact index object behind the C ABI - the library-owned counterpart of
+// faiss.IndexFlatIP as the reference drives it (VectorStore_Faiss.py:110-148 create, :169-178,202
+// add, :258-263 search, :385-419 delete -> remove_ids).  It owns the row matrix in HBM (storage
+// dtype, rows normalised at add time when the metric is cosine), grows it geometrically, keeps its
+// own workspace and staging buffers, and accepts fp32 inputs and outputs either as device pointers
+// or as plain HOST buffers - a host that is not PyTorch (or not Python) needs nothing else.
+// All arithmetic is the stateless entry points' (ragarc_normalize_cast, ragarc_dense_topk).
+#include <mutex>
+#include <new>
+#include <vector>
+#include "common.cuh"
+
+struct ragarc_index {
+  int d = 0, dtype = RAGARC_F32, metric = RAGARC_METRIC_IP, device = 0;
+  void* rows = nullptr;           // [cap, d] storage dtype
+  int64_t n = 0, cap = 0;
+  void* ws = nullptr;             // dense_topk workspace
+  size_t ws_bytes = 0;
+  void* stage = nullptr;          // device staging: fp32 inputs, prepared queries, results
+  size_t stage_bytes = 0;
+  cudaEvent_t last = nullptr;     // end of the previous call's GPU work (calls may come on different streams)
+  std::mutex mu;
+};
+
+namespace ragarc {
+
+static size_t esize(int dtype) { return dtype == RAGARC_F32 ? 4 : 2; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int grow_buffer(void** buf, size_t* have, size_t need, cudaStream_t st) {
+  if (*have >= need) return RAGARC_OK;
+  (void)st;
+  RA_CUDA(cudaDeviceSynchronize());            // nothing in flight may still use the old buffer
+  if (*buf) RA_CUDA(cudaFree(*buf));
+  *buf = nullptr; *have = 0;
+  size_t want = need + need / 4;
+  RA_CUDA(cudaMalloc(buf, want));
+  *have = want;
+  return RAGARC_OK;
+}
+
+static int reserve_rows(ragarc_index* ix, int64_t capacity, cudaStream_t st) {
+  if (capacity <= ix->cap) return RAGARC_OK;
+  int64_t cap = ix->cap > 0 ? ix->cap : 1024;
+  while (cap < capacity) cap += cap / 2 + 1024;          // geometric growth: O(1) amortised copies
+  if (capacity > ix->cap * 4) cap = capacity;            // bulk load: exact size, no slack
+  void* fresh = nullptr;
+  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  RA_CUDA(cudaMalloc(&fresh, (size_t)cap * row_bytes));
+  if (ix->n > 0) RA_CUDA(cudaMemcpyAsync(fresh, ix->rows, (size_t)ix->n * row_bytes, cudaMemcpyDeviceToDevice, st));
+  RA_CUDA(cudaDeviceSynchronize());
+  if (ix->rows) RA_CUDA(cudaFree(ix->rows));
+  ix->rows = fresh;
+  ix->cap = cap;
+  return RAGARC_OK;
+}
+
+// calls on one index are ordered on the GPU even when they arrive on different streams
+static int order_begin(ragarc_index* ix, cudaStream_t st) {
+  RA_CUDA(cudaStreamWaitEvent(st, ix->last, 0));
+  return RAGARC_OK;
+}
+static int order_end(ragarc_index* ix, cudaStream_t st) {
+  RA_CUDA(cudaEventRecord(ix->last, st));
+  return RAGARC_OK;
+}
+
+// rows of a new matrix gathered from an old one: dst[i] = src[map[i]]   (16-byte words when possible)
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                   const int64_t* __restrict__ map, int64_t n_out, int row_bytes) {
+  const int64_t row = blockIdx.x;
+  if (row >= n_out) return;
+  const uint8_t* s = src + (size_t)map[row] * row_bytes;
+  uint8_t* o = dst + (size_t)row * row_bytes;
+  if ((row_bytes & 15) == 0) {
+    for (int i = threadIdx.x; i < (row_bytes >> 4); i += blockDim.x)
+      reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) o[i] = s[i];
+  }
+}
+
+}  // namespace ragarc
+
+using namespace ragarc;
+
+extern "C" {
+
+int ragarc_index_create(int d, int dtype, int metric, ragarc_index_t** out) {
+  RA_REQUIRE(out != nullptr, "index_create: out is NULL");
+  *out = nullptr;
+  RA_REQUIRE(d > 0, "index_create: d=%d", d);
+  RA_REQUIRE(dtype == RAGARC_F32 || dtype == RAGARC_BF16 || dtype == RAGARC_F16, "index_create: bad dtype %d", dtype);
+  RA_REQUIRE(metric == RAGARC_METRIC_IP || metric == RAGARC_METRIC_COSINE, "index_create: bad metric %d", metric);
+  int dev = 0;
+  RA_CUDA(cudaGetDevice(&dev));
+  ragarc_index* ix = new (std::nothrow) ragarc_index();
+  RA_REQUIRE(ix != nullptr, "index_create: out of host memory");
+  ix->d = d; ix->dtype = dtype; ix->metric = metric; ix->device = dev;
+  if (cudaEventCreateWithFlags(&ix->last, cudaEventDisableTiming) != cudaSuccess) {
+    delete ix;
+    set_error("index_create: cannot create a CUDA event: %s", cudaGetErrorString(cudaGetLastError()));
+    return RAGARC_ERR_CUDA;
+  }
+  *out = ix;
+  return RAGARC_OK;
+}
+
+int ragarc_index_free(ragarc_index_t* ix) {
+  if (!ix) return RAGARC_OK;
+  {
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->rows) cudaFree(ix->rows);
+    if (ix->ws) cudaFree(ix->ws);
+    if (ix->stage) cudaFree(ix->stage);
+    if (ix->last) cudaEventDestroy(ix->last);
+  }
+  delete ix;
+  return RAGARC_OK;
+}
+
+int64_t ragarc_index_ntotal(const ragarc_index_t* ix) { return ix ? ix->n : -1; }
+int ragarc_index_dim(const ragarc_index_t* ix) { return ix ? ix->d : -1; }
+const void* ragarc_index_rows(const ragarc_index_t* ix) { return ix ? ix->rows : nullptr; }
+
+int ragarc_index_reserve(ragarc_index_t* ix, int64_t capacity, void* stream) {
+  RA_REQUIRE(ix != nullptr, "index_reserve: null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  RA_REQUIRE(g.ok, "index_reserve: cannot select device %d", ix->device);
+  return reserve_rows(ix, capacity, (cudaStream_t)stream);
+}
+
+int ragarc_index_add(ragarc_index_t* ix, const float* rows, int64_t n, int rows_on_host, void* stream) {
+  RA_REQUIRE(ix != nullptr, "index_add: null index");
+  RA_REQUIRE(n >= 0, "index_add: n=%lld", (long long)n);
+  if (n == 0) return RAGARC_OK;
+  RA_REQUIRE(rows != nullptr, "index_add: null rows");
+  RA_REQUIRE(ix->n + n < (int64_t)0xFFFFFFF0ll, "index_add: at most 2^32-16 rows per index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  RA_REQUIRE(g.ok, "index_add: cannot select device %d", ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = order_begin(ix, st);
+  if (rc) return rc;
+  rc = reserve_rows(ix, ix->n + n, st);
+  if (rc) return rc;
+  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  const int normalize = ix->metric == RAGARC_METRIC_COSINE;
+  if (!rows_on_host) {
+    rc = ragarc_normalize_cast(rows, (char*)ix->rows + (size_t)ix->n * row_bytes, n, ix->d, ix->dtype, normalize, stream);
+    if (rc) return rc;
+  } else {
+    // host rows travel through a bounded device staging buffer (<= 256 MB of fp32 at a time)
+    int64_t chunk = (int64_t)((256ull << 20) / ((size_t)ix->d * 4));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    rc = grow_buffer(&ix->stage, &ix->stage_bytes, (size_t)chunk * ix->d * 4, st);
+    if (rc) return rc;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+      const int64_t c = n - r0 < chunk ? n - r0 : chunk;
+      RA_CUDA(cudaMemcpyAsync(ix->stage, rows + (size_t)r0 * ix->d, (size_t)c * ix->d * 4, cudaMemcpyHostToDevice, st));
+      rc = ragarc_normalize_cast((const float*)ix->stage, (char*)ix->rows + (size_t)(ix->n + r0) * row_bytes, c, ix->d,
+                                 ix->dtype, normalize, stream);
+      if (rc) return rc;
+    }
+    RA_CUDA(cudaStreamSynchronize(st));        // the caller may reuse its host buffer on return
+  }
+  ix->n += n;
+  return order_end(ix, st);
+}
+
+int ragarc_index_search(ragarc_index_t* ix, const float* queries, int nq, int k, float* out_scores,
+                        int64_t* out_ids, int buffers_on_host, void* stream) {
+  RA_REQUIRE(ix != nullptr, "index_search: null index");
+  RA_REQUIRE(nq >= 0 && k > 0, "index_search: nq=%d k=%d", nq, k);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(queries && out_scores && out_ids, "index_search: null pointer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  RA_REQUIRE(g.ok, "index_search: cannot select device %d", ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t q32_bytes = align_up((size_t)nq * ix->d * 4, 256);
+  const size_t qs_bytes = align_up((size_t)nq * ix->d * esize(ix->dtype), 256);
+  const size_t os_bytes = align_up((size_t)nq * k * 4, 256);
+  const size_t oi_bytes = align_up((size_t)nq * k * 8, 256);
+  int rc = order_begin(ix, st);
+  if (rc) return rc;
+  rc = grow_buffer(&ix->stage, &ix->stage_bytes, q32_bytes + qs_bytes + os_bytes + oi_bytes, st);
+  if (rc) return rc;
+  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->d, ix->dtype, nq, k);
+  RA_REQUIRE(need_ws > 0, "index_search: unsupported shape (k=%d)", k);
+  rc = grow_buffer(&ix->ws, &ix->ws_bytes, need_ws, st);
+  if (rc) return rc;
+  char* sg = (char*)ix->stage;
+  float* q32 = (float*)sg;
+  void* qs = sg + q32_bytes;
+  float* d_scores = buffers_on_host ? (float*)(sg + q32_bytes + qs_bytes) : out_scores;
+  int64_t* d_ids = buffers_on_host ? (int64_t*)(sg + q32_bytes + qs_bytes + os_bytes) : out_ids;
+  const float* q_src = queries;
+  if (buffers_on_host) {
+    RA_CUDA(cudaMemcpyAsync(q32, queries, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+    q_src = q32;
+  }
+  // faiss.normalize_L2 on the query when the metric is cosine (VectorStore_Faiss.py:259), then the
+  // cast to the storage dtype; for fp32 storage without normalisation the queries are used in place
+  const void* q_use = q_src;
+  if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
+    rc = ragarc_normalize_cast(q_src, qs, nq, ix->d, ix->dtype, ix->metric == RAGARC_METRIC_COSINE, stream);
+    if (rc) return rc;
+    q_use = qs;
+  }
+  rc = ragarc_dense_topk(ix->rows, ix->n, ix->d, ix->dtype, q_use, nq, k, d_scores, d_ids, ix->ws, ix->ws_bytes,
+                         RAGARC_DENSE_AUTO, nullptr, stream);
+  if (rc) return rc;
+  if (buffers_on_host) {
+    RA_CUDA(cudaMemcpyAsync(out_scores, d_scores, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    RA_CUDA(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    RA_CUDA(cudaStreamSynchronize(st));
+  }
+  return order_end(ix, st);
+}
+
+int ragarc_index_remove(ragarc_index_t* ix, const int64_t* rows_host, int64_t n_remove, void* stream) {
+  RA_REQUIRE(ix != nullptr, "index_remove: null index");
+  RA_REQUIRE(n_remove >= 0, "index_remove: n_remove=%lld", (long long)n_remove);
+  if (n_remove == 0) return RAGARC_OK;
+  RA_REQUIRE(rows_host != nullptr, "index_remove: null rows");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  RA_REQUIRE(g.ok, "index_remove: cannot select device %d", ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = order_begin(ix, st);
+  if (rc) return rc;
+  std::vector<uint8_t> drop((size_t)ix->n, 0);
+  for (int64_t i = 0; i < n_remove; ++i) {
+    RA_REQUIRE(rows_host[i] >= 0 && rows_host[i] < ix->n, "index_remove: row %lld out of range [0,%lld)",
+               (long long)rows_host[i], (long long)ix->n);
+    drop[(size_t)rows_host[i]] = 1;
+  }
+  // survivors keep their relative order and are renumbered densely (faiss remove_ids semantics,
+  // which VectorStore_Faiss.py:403-412 mirrors in index_to_docstore_id)
+  std::vector<int64_t> map;
+  map.reserve((size_t)ix->n);
+  for (int64_t r = 0; r < ix->n; ++r) if (!drop[(size_t)r]) map.push_back(r);
+  const int64_t n_out = (int64_t)map.size();
+  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  void* fresh = nullptr;
+  int64_t* d_map = nullptr;
+  const int64_t cap = n_out > 0 ? n_out : 1;
+  RA_CUDA(cudaMalloc(&fresh, (size_t)cap * row_bytes));
+  if (n_out > 0) {
+    RA_CUDA(cudaMalloc((void**)&d_map, (size_t)n_out * 8));
+    RA_CUDA(cudaMemcpyAsync(d_map, map.data(), (size_t)n_out * 8, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<(unsigned)n_out, 128, 0, st>>>((const uint8_t*)ix->rows, (uint8_t*)fresh, d_map, n_out, (int)row_bytes);
+    RA_LAUNCH_CHECK();
+  }
+  RA_CUDA(cudaDeviceSynchronize());
+  if (d_map) RA_CUDA(cudaFree(d_map));
+  if (ix->rows) RA_CUDA(cudaFree(ix->rows));
+  ix->rows = fresh;
+  ix->cap = cap;
+  ix->n = n_out;
+  return order_end(ix, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+"""``NativeFlatIndex``: the library-owned flat index (``ragarc_index_*`` in include/ragarc_b200.h)
+driven with plain numpy host buffers - no torch tensor on the path.
+
+This is what a host that is not PyTorch sees: create, ``add`` fp32 rows, ``search`` fp32 queries,
+``remove`` rows, exactly the calls ``FaissVectorStore`` makes on ``faiss.IndexFlatIP``
+(VectorStore_Faiss.py:114-115 create, :178,202 normalise + add, :259-263 normalise + search,
+:385-419 remove_ids).  Device memory, workspace and staging live inside the handle.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+
+_DTYPES = {"float32": N.F32, "bfloat16": N.BF16, "float16": N.F16}
+_METRICS = {"ip": N.METRIC_IP, "cosine": N.METRIC_COSINE}
+
+
+class NativeFlatIndex:
+    def __init__(self, d: int, dtype: str = "float32", metric: str = "cosine"):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        if metric not in _METRICS:
+            raise ValueError(f"metric must be one of {sorted(_METRICS)} (exact inner product / cosine only)")
+        self.d, self.dtype, self.metric = int(d), dtype, metric
+        h = ctypes.c_void_p()
+        N.check(N.lib.ragarc_index_create(self.d, _DTYPES[dtype], _METRICS[metric], ctypes.byref(h)), "index_create")
+        self._h = h
+
+    # faiss.IndexFlatIP.ntotal
+    @property
+    def ntotal(self) -> int:
+        return int(N.lib.ragarc_index_ntotal(self._h))
+
+    def reserve(self, capacity: int) -> None:
+        N.check(N.lib.ragarc_index_reserve(self._h, int(capacity), None), "index_reserve")
+
+    def add(self, x: np.ndarray) -> None:
+        """x: float32 [n, d] host array (normalised inside when the metric is cosine)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"expected [n,{self.d}] float32 rows")
+        N.check(N.lib.ragarc_index_add(self._h, x.ctypes.data, x.shape[0], 1, None), "index_add")
+
+    def search(self, q: np.ndarray, k: int):
+        """q: float32 [nq, d] host array -> (D float32 [nq,k] descending, I int64 [nq,k], -1 padded):
+        the return contract of ``faiss.IndexFlatIP.search``."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise ValueError(f"expected [nq,{self.d}] float32 queries")
+        D = np.empty((q.shape[0], k), np.float32)
+        I = np.empty((q.shape[0], k), np.int64)
+        N.check(N.lib.ragarc_index_search(self._h, q.ctypes.data, q.shape[0], int(k), D.ctypes.data,
+                                          I.ctypes.data, 1, None), "index_search")
+        return D, I
+
+    def remove(self, rows) -> int:
+        """Drops the given row numbers; survivors are renumbered densely in order (remove_ids)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64).ravel()
+        before = self.ntotal
+        N.check(N.lib.ragarc_index_remove(self._h, rows.ctypes.data, rows.shape[0], None), "index_remove")
+        return before - self.ntotal
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            N.lib.ragarc_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

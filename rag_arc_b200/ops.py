@@ -217,7 +217,26 @@ def bm25_topk(index, q_terms: torch.Tensor, q_len: torch.Tensor, k: int, use_pos
                                        q_terms.data_ptr(), q_len.data_ptr(), nq, tmax, index.n_docs, k,
                                        scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(),
                                        _stream_ptr(dev)), "bm25_topk")
+    base = int(getattr(index, "id_base", 0))
+    if base:
+        ids = torch.where(ids >= 0, ids + base, ids)     # shard-local doc ids -> global
     return scores, ids
+
+
+def bm25_merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+    """scores float64 / ids int64 ``[n_lists, nq, k_in]`` (per-shard BM25 results carrying global doc
+    ids, -1 padding) -> global top-k_out per query (scores float64 [nq,k_out], ids int64)."""
+    _cuda(scores, "scores"); _cuda(ids, "ids")
+    if scores.dtype != torch.float64 or ids.dtype != torch.int64 or scores.shape != ids.shape or scores.dim() != 3:
+        raise N.RagArcError("bm25_merge_topk expects float64 scores and int64 ids of shape [n_lists, nq, k_in]")
+    G, nq, k_in = scores.shape
+    dev = scores.device
+    out_s = torch.empty((nq, k_out), dtype=torch.float64, device=dev)
+    out_i = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_bm25_merge_topk(scores.data_ptr(), ids.data_ptr(), G, nq, k_in, k_out,
+                                             out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(dev)), "bm25_merge_topk")
+    return out_s, out_i
 
 
 def bm25_scores(index, q_terms: torch.Tensor, q_len: torch.Tensor, use_post_val: bool = True) -> torch.Tensor:

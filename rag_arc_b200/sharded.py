@@ -154,3 +154,62 @@ class ShardedFlatIndex:
         dist.all_gather_into_tensor(buf.view(-1), keys.view(-1), group=self.group)
         self.exchange_used = "nccl"
         return ops.merge_topk_keys(buf, k)
+
+
+class ShardedBm25Index:
+    """Doc-range sharded BM25: rank g scores the documents
+    ``shard_bounds(N, G, g)`` with the GLOBAL idf / average length, the per-shard top-k (fp64 scores,
+    global doc ids) are all-gathered (one collective: scores and ids packed into one int64 block of
+    ``2*nq*k*8`` bytes per rank) and merged on every rank by ``ragarc_bm25_merge_topk``.  The merged
+    result is bit-identical to the single-index one: the score of a document never depends on which
+    shard holds it, and ties break towards the lowest global doc id in both.
+
+    The reference scores BM25 on one host only (core/retrieval/bm25.py:297-311)."""
+
+    def __init__(self, full_index, device, group=None):
+        """full_index: a ``Bm25Index`` of the WHOLE corpus built on the host (``device=None``) - every
+        rank builds or loads the same one, as it needs the global statistics anyway."""
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_docs = full_index.n_docs
+        lo, hi = shard_bounds(full_index.n_docs, self.world, self.rank)
+        self.local = full_index.shard(lo, hi, device)
+        self.full = full_index
+        self._buf = None
+
+    def encode_queries(self, queries):
+        return self.local.encode_queries(queries)
+
+    def encode_query_ids(self, qids):
+        return self.local.encode_query_ids(qids)
+
+    def search(self, q_terms: torch.Tensor, q_len: torch.Tensor, k: int):
+        """Returns ``(scores float64 [nq,k], global doc ids int64 [nq,k])`` on every rank."""
+        nq = q_terms.shape[0]
+        kk = min(k, self.n_docs)
+        k_loc = max(1, min(kk, self.local.n_docs)) if self.local.n_docs > 0 else 1
+        if self.local.n_docs > 0:
+            s, i = ops.bm25_topk(self.local, q_terms, q_len, k_loc)
+        else:                                          # more ranks than documents: nothing to offer
+            s = torch.full((nq, k_loc), float("-inf"), dtype=torch.float64, device=q_terms.device)
+            i = torch.full((nq, k_loc), -1, dtype=torch.int64, device=q_terms.device)
+        # every rank contributes a [2, nq, kk] block (padded when its shard is smaller than kk)
+        mine = torch.full((2, nq, kk), -1, dtype=torch.int64, device=q_terms.device)
+        mine[0, :, :k_loc] = s.view(torch.int64)
+        mine[1, :, :k_loc] = i
+        if self.world == 1:
+            allb = mine.view(1, 2, nq, kk)
+        else:
+            if self._buf is None or self._buf.shape != (self.world, 2, nq, kk) or self._buf.device != mine.device:
+                self._buf = torch.empty((self.world, 2, nq, kk), dtype=torch.int64, device=mine.device)
+            dist.all_gather_into_tensor(self._buf.view(-1), mine.view(-1), group=self.group)
+            allb = self._buf
+        scores = allb[:, 0].contiguous().view(torch.float64)
+        ids = allb[:, 1].contiguous()
+        out_s, out_i = ops.bm25_merge_topk(scores, ids, kk)
+        if kk < k:                                     # k > number of documents: pad like the single index
+            pad_s = torch.full((nq, k - kk), float("-inf"), dtype=torch.float64, device=out_s.device)
+            pad_i = torch.full((nq, k - kk), -1, dtype=torch.int64, device=out_i.device)
+            out_s, out_i = torch.cat([out_s, pad_s], 1), torch.cat([out_i, pad_i], 1)
+        return out_s, out_i

@@ -78,3 +78,79 @@ def test_sharded_search_two_ranks_gloo_equals_single_shot(n, k):
         p.join(120)
         assert p.exitcode == 0
     assert out.get() == 1
+
+
+# ---- doc-range sharded BM25 ----------------------------------------------------------------------
+def _fake_bm25_topk(index, q_terms, q_len, k, use_post_val=True):
+    """numpy stand-in for ragarc_bm25_topk over the shard's own arrays (reference operation order)."""
+    from oracle import bm25 as obm25
+    qt = q_terms.numpy(); ql = q_len.numpy()
+    nq = qt.shape[0]
+    S = np.full((nq, k), -np.inf); I = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        sc = np.zeros(index.n_docs)
+        for t in qt[q, :ql[q]]:
+            if t < 0:
+                continue
+            a, b = index.indptr_np[t], index.indptr_np[t + 1]
+            sc[index.post_doc_np[a:b]] += index.idf_np[t] * index.post_val_np[a:b]
+        top = obm25.stable_topk(sc, min(k, index.n_docs))
+        S[q, :len(top)] = sc[top]; I[q, :len(top)] = top + index.id_base
+    return torch.from_numpy(S), torch.from_numpy(I)
+
+
+def _fake_bm25_merge(scores, ids, k_out):
+    G, nq, k = scores.shape
+    s = scores.numpy().transpose(1, 0, 2).reshape(nq, G * k)
+    i = ids.numpy().transpose(1, 0, 2).reshape(nq, G * k)
+    out_s = np.full((nq, k_out), -np.inf); out_i = np.full((nq, k_out), -1, np.int64)
+    for q in range(nq):
+        valid = np.flatnonzero(i[q] >= 0)
+        order = valid[np.lexsort((i[q][valid], -s[q][valid]))][:k_out]
+        out_s[q, :len(order)] = s[q][order]; out_i[q, :len(order)] = i[q][order]
+    return torch.from_numpy(out_s), torch.from_numpy(out_i)
+
+
+def _bm25_worker(rank, world, port, n_docs, k, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import bm25 as obm25
+    from rag_arc_b200 import ops, sharded
+    from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
+    ops.bm25_topk = _fake_bm25_topk
+    ops.bm25_merge_topk = _fake_bm25_merge
+    rng = np.random.default_rng(3)
+    words = [f"w{i}" for i in range(40)]
+    corpus = [[words[j] for j in rng.integers(0, 40, rng.integers(1, 12))] for _ in range(n_docs)]
+    queries = [[words[j] for j in rng.integers(0, 40, 4)] + ["unseen"] for _ in range(6)]
+    full = Bm25Index.from_token_lists(corpus, device=None)
+    idx = sharded.ShardedBm25Index(full, "cpu")
+    qt, ql = idx.encode_queries(queries)
+    scores, ids = idx.search(qt, ql, k)
+    ref = obm25.BM25Okapi(corpus)
+    ok = True
+    for qi, q in enumerate(queries):
+        want = ref.get_scores(q)
+        top = obm25.stable_topk(want, min(k, n_docs))
+        ok &= ids[qi, :len(top)].tolist() == top.tolist()
+        ok &= np.array_equal(scores[qi, :len(top)].numpy().view(np.uint64), want[top].view(np.uint64))
+        ok &= bool((ids[qi, len(top):] == -1).all())
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_docs,k", [(101, 10), (3, 5)])
+def test_sharded_bm25_two_ranks_gloo_equals_single_index(n_docs, k):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bm25_worker, args=(r, 2, port, n_docs, k, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() == 1

@@ -56,3 +56,43 @@ def test_sharded_search_equals_single_gpu(exchange):
         assert p.exitcode == 0
     ok, used = out.get()
     assert ok == 1, f"mismatch (exchange used: {used})"
+
+
+def _bm25_worker(rank, world, port, out):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from rag_arc_b200 import ops, sharded, synth
+    from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
+    toks, offs = synth.bm25_corpus_tokens(50_001, vocab=8000, seed=13)
+    full = Bm25Index.from_token_ids(toks, offs, device=None)
+    single = Bm25Index.from_token_ids(toks, offs, device=dev)
+    idx = sharded.ShardedBm25Index(full, dev)
+    qt, ql = idx.encode_query_ids(synth.bm25_queries_tokens(toks, offs, 64, 8, seed=14))
+    s, i = idx.search(qt, ql, 50)
+    s_ref, i_ref = ops.bm25_topk(single, qt, ql, 50)
+    ok = bool(torch.equal(i, i_ref) and torch.equal(s.view(torch.int64), s_ref.view(torch.int64)))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_bm25_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bm25_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert out.get() == 1

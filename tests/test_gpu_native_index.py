@@ -1,0 +1,81 @@
+"""GPU: the library-owned flat index (``ragarc_index_*``) driven through ctypes with numpy HOST
+buffers only - the calls FaissVectorStore makes on faiss.IndexFlatIP (VectorStore_Faiss.py:114-115,
+178, 202, 259-263, 385-419) - against the oracle restatement of that index."""
+import numpy as np
+import pytest
+
+from oracle import dense as odense
+from oracle.compare import check_topk_against_scores
+from rag_arc_b200 import synth
+from rag_arc_b200.native_index import NativeFlatIndex
+
+pytestmark = pytest.mark.gpu
+
+
+def _round_bf16(a):
+    u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_fp32_cosine_index_matches_faiss_restatement_c1(dev):
+    """BASELINE config 1 through the handle API: un-normalised fp32 rows in, cosine metric."""
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((10_000, 384)).astype(np.float32) * 3.0
+    Q = (X[rng.integers(0, 10_000, 100)] + 0.3 * rng.standard_normal((100, 384))).astype(np.float32)
+    ix = NativeFlatIndex(384, "float32", "cosine")
+    ix.add(X[:3000]); ix.add(X[3000:3001]); ix.add(X[3001:])          # grows twice
+    assert ix.ntotal == 10_000
+    D, I = ix.search(Q, 10)
+    Xn, Qn = X.copy(), Q.copy()
+    odense.normalize_L2(Xn); odense.normalize_L2(Qn)          # in place, like faiss.normalize_L2
+    Dref, Iref = odense.flat_ip_search(Xn, Qn, 10)
+    assert (I == Iref).all()
+    assert np.allclose(D, Dref, rtol=1e-5, atol=1e-5)
+    ix.close()
+
+
+def test_bf16_ip_index_and_k_larger_than_ntotal(dev):
+    X = synth.dense_corpus_np(5000, 256, seed=3)
+    Q, planted = synth.dense_queries_np(X, 33, seed=4)
+    ix = NativeFlatIndex(256, "bfloat16", "ip")
+    ix.add(X)
+    D, I = ix.search(Q, 20)
+    S = _round_bf16(Q).astype(np.float64) @ _round_bf16(X).astype(np.float64).T
+    for i in range(33):
+        check_topk_against_scores(I[i], D[i], S[i], 20, rtol=1e-5, atol=1e-5, what=f"q{i}")
+    assert (I[:, 0] == planted).all()
+    small = NativeFlatIndex(256, "bfloat16", "ip")
+    small.add(X[:7])
+    D, I = small.search(Q[:2], 12)
+    assert (I[:, 7:] == -1).all() and np.isinf(D[:, 7:]).all()
+    assert sorted(I[0, :7].tolist()) == list(range(7))
+
+
+def test_remove_renumbers_like_faiss_remove_ids(dev):
+    X = synth.dense_corpus_np(2000, 128, seed=9)
+    Q, _ = synth.dense_queries_np(X, 16, seed=10)
+    ix = NativeFlatIndex(128, "float32", "ip")
+    ix.add(X)
+    drop = np.array([5, 0, 1999, 700, 5, 701])
+    assert ix.remove(drop) == 5
+    keep = np.setdiff1d(np.arange(2000), drop)
+    D, I = ix.search(Q, 8)
+    Dref, Iref = odense.flat_ip_search(X[keep], Q, 8)
+    assert (I == Iref).all() and np.allclose(D, Dref, rtol=1e-5, atol=1e-5)
+    ix.add(X[:3])                                                      # appended after the survivors
+    assert ix.ntotal == 1998
+    D, I = ix.search(X[:1], 2)
+    assert 1995 in I[0].tolist()
+
+
+def test_bad_arguments_fail_loudly(dev):
+    from rag_arc_b200._native import RagArcError
+    with pytest.raises(ValueError):
+        NativeFlatIndex(64, "float32", "l2")
+    ix = NativeFlatIndex(64, "float32", "ip")
+    ix.add(np.zeros((4, 64), np.float32))
+    with pytest.raises(RagArcError):
+        ix.remove([9])
+    with pytest.raises(ValueError):
+        ix.add(np.zeros((4, 32), np.float32))

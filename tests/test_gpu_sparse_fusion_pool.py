@@ -70,6 +70,30 @@ def test_bm25_c2_shape_bit_exact_against_csr_oracle(dev):
     assert torch.equal(full_a.view(torch.int64), full_b.view(torch.int64))
 
 
+def test_bm25_doc_range_shards_merge_to_the_single_index_result(dev):
+    """Three uneven doc-range shards (global idf / avgdl), per-shard top-k, ragarc_bm25_merge_topk:
+    bit-identical to the unsharded search - the multi-GPU arithmetic on one device."""
+    toks, offs = synth.bm25_corpus_tokens(30_000, vocab=6000, seed=21)
+    full = Bm25Index.from_token_ids(toks, offs, device=None)
+    single = Bm25Index.from_token_ids(toks, offs, device=dev)
+    qt, ql = single.encode_query_ids(synth.bm25_queries_tokens(toks, offs, 40, 8, seed=22))
+    for k in (20, 700):
+        s_ref, i_ref = ops.bm25_topk(single, qt, ql, k)
+        parts = []
+        for lo, hi in ((0, 11_000), (11_000, 11_300), (11_300, 30_000)):
+            sh = full.shard(lo, hi, dev)
+            kk = min(k, hi - lo)
+            s, i = ops.bm25_topk(sh, qt, ql, kk)
+            ps = torch.full((40, k), float("-inf"), dtype=torch.float64, device=dev)
+            pi = torch.full((40, k), -1, dtype=torch.int64, device=dev)
+            ps[:, :kk] = s; pi[:, :kk] = i
+            parts.append((ps, pi))
+        s, i = ops.bm25_merge_topk(torch.stack([p[0] for p in parts]).contiguous(),
+                                   torch.stack([p[1] for p in parts]).contiguous(), k)
+        assert torch.equal(i, i_ref)
+        assert torch.equal(s.view(torch.int64), s_ref.view(torch.int64))
+
+
 def test_bm25_fewer_matches_than_k_fills_with_zero_score_docs(dev):
     toks = [["a", "b"], ["c"], ["d"], ["e"], ["a"], ["f"]]
     idx = Bm25Index.from_token_lists(toks, device=dev)
