@@ -213,3 +213,85 @@ class ShardedBm25Index:
             pad_i = torch.full((nq, k - kk), -1, dtype=torch.int64, device=out_i.device)
             out_s, out_i = torch.cat([out_s, pad_s], 1), torch.cat([out_i, pad_i], 1)
         return out_s, out_i
+
+
+class ShardedSearchPipeline:
+    """Host-in / host-out batched search over a ``ShardedFlatIndex`` for throughput: the whole
+    per-rank step (query normalise + cast, seeding, scoring, key exchange, merge) of each of two
+    staging slots is a CUDA graph, and the H2D copy of batch i+1 and the D2H copy of batch i-1 run
+    on their own streams while the graph of batch i executes - every batch still moves its own
+    queries in and its own results out.  Every rank must submit the same batches in the same order.
+
+        pipe = ShardedSearchPipeline(sharded, flat_index.prepare_queries, nq, d, k)
+        t = pipe.submit(q_host_fp32_pinned)
+        scores, rows = pipe.result(t)           # pinned host tensors (valid until the slot is reused)
+
+    The two graphs are bound to the two exchange-buffer slots of the peer-memory path, so while a
+    pipeline is in use the index must not be searched through any other route (a full
+    ``dist.barrier()`` + device synchronise separates it from earlier work)."""
+
+    def __init__(self, index: ShardedFlatIndex, prepare, nq: int, d: int, k: int):
+        self.index, self.nq, self.k = index, nq, k
+        dev = index.rows.device
+        self.dev = dev
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        q32s = [torch.zeros((nq, d), dtype=torch.float32, device=dev) for _ in range(2)]
+        for q32 in q32s:                                   # allocations, peer rendezvous
+            index.search(prepare(q32), k)
+        torch.cuda.synchronize(dev)
+        if index.world > 1:
+            dist.barrier(group=index.group)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        self.slots = []
+        with torch.cuda.stream(side):
+            for q32 in q32s:                               # workspaces of the capture stream exist now
+                index.search(prepare(q32), k)
+            side.synchronize()
+            for q32 in q32s:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    scores, rows = index.search(prepare(q32), k)
+                self.slots.append({
+                    "q32": q32, "graph": g, "scores": scores, "rows": rows,
+                    "h_scores": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                    "h_rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                    "copied_in": torch.cuda.Event(), "computed": torch.cuda.Event(),
+                    "copied_out": torch.cuda.Event(), "busy": False,
+                })
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if index.world > 1:
+            dist.barrier(group=index.group)
+        self.n_submitted = 0
+
+    def submit(self, q_host: torch.Tensor) -> int:
+        ticket = self.n_submitted
+        slot = self.slots[ticket & 1]
+        if slot["busy"]:
+            raise RuntimeError("pipeline slot still in use: call result() for older tickets first")
+        if q_host.shape != slot["q32"].shape or q_host.dtype != torch.float32:
+            raise ValueError(f"expected float32 {tuple(slot['q32'].shape)} queries")
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(slot["computed"])        # the slot's previous batch has consumed q32
+            slot["q32"].copy_(q_host, non_blocking=True)
+            slot["copied_in"].record(self.s_in)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(slot["copied_in"])
+            self.s_cmp.wait_event(slot["copied_out"])     # the slot's previous results have left
+            slot["graph"].replay()
+            slot["computed"].record(self.s_cmp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["computed"])
+            slot["h_scores"].copy_(slot["scores"], non_blocking=True)
+            slot["h_rows"].copy_(slot["rows"], non_blocking=True)
+            slot["copied_out"].record(self.s_out)
+        slot["busy"] = True
+        self.n_submitted += 1
+        return ticket
+
+    def result(self, ticket: int):
+        slot = self.slots[ticket & 1]
+        slot["copied_out"].synchronize()
+        slot["busy"] = False
+        return slot["h_scores"], slot["h_rows"]

@@ -96,3 +96,53 @@ def test_sharded_bm25_equals_single_gpu():
         p.join(300)
         assert p.exitcode == 0
     assert out.get() == 1
+
+
+def _pipe_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from rag_arc_b200 import ops, sharded, synth
+    n, d, nq, k = 200_000, 128, 96, 20
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=3)
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    idx = sharded.ShardedFlatIndex(x[lo:hi].contiguous(), lo)
+    prepare = lambda q32: ops.normalize_cast(q32, torch.bfloat16, True)
+    pipe = sharded.ShardedSearchPipeline(idx, prepare, nq, d, k)
+    batches = [torch.randn((nq, d), generator=torch.Generator().manual_seed(100 + i)).pin_memory() for i in range(5)]
+    ok, prev = True, None
+    results = []
+    for b in batches:
+        t = pipe.submit(b)
+        if prev is not None:
+            s, r = pipe.result(prev)
+            results.append((s.clone(), r.clone()))
+        prev = t
+    s, r = pipe.result(prev)
+    results.append((s.clone(), r.clone()))
+    for b, (s, r) in zip(batches, results):
+        s_ref, r_ref = ops.dense_topk(x, prepare(b.to(dev)), k)
+        ok = ok and bool(torch.equal(r, r_ref.cpu()) and torch.equal(s, s_ref.cpu()))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_pipeline_host_in_host_out_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert out.get() == 1
