@@ -41,7 +41,7 @@ enum {
 };
 
 /* storage dtype of corpus / query / encoder matrices */
-enum { RAGARC_F32 = 0, RAGARC_BF16 = 1, RAGARC_F16 = 2 };
+enum { RAGARC_F32 = 0, RAGARC_BF16 = 1, RAGARC_F16 = 2, RAGARC_F64 = 3 /* adjacent_cosine_distance only */ };
 
 /* pooling modes (sentence-transformers Pooling module) */
 enum { RAGARC_POOL_MEAN = 0, RAGARC_POOL_CLS = 1, RAGARC_POOL_LAST = 2 };
@@ -229,6 +229,27 @@ int ragarc_pool_normalize(const void* x, int dtype, const int32_t* mask, int B, 
 int ragarc_mmr_select(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                       int nq, const int64_t* cand_rows, int fetch_k, int k, double lambda_mult,
                       int32_t* out_sel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cosine distance between consecutive rows.   Replaces calculate_cosine_distances at
+ *   core/file_management/chunker/spliter.py:354-372 (SemanticChunker), which calls the row-wise
+ *   cosine_similarity of :307-333 once per adjacent pair in Python.
+ * x: [n,d] fp32 or fp64 row-major; out[i] = 1 - <x_i,x_{i+1}> / (|x_i| |x_{i+1}|) for i < n-1,
+ * evaluated in fp64 like the numpy fallback of the reference; a nan/inf similarity (zero row)
+ * counts as 0, i.e. distance 1.
+ */
+int ragarc_adjacent_cosine_distance(const void* x, int dtype, int64_t n, int d, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Reranker scoring tail.   Replaces Qwen3Reranker.compute_logits after the LM forward at
+ *   core/rerank/Reranker_Qwen3.py:44-49: pick the "yes"/"no" logits of the last position,
+ *   log_softmax over the two, exp of the "yes" entry.
+ * logits: [B, vocab] rows of the last position (row_stride elements apart), in `dtype`; the two
+ * intermediate results are rounded to `dtype` as the reference's tensor library does; out: fp32 [B] (values exactly
+ * representable in `dtype`).
+ */
+int ragarc_yes_no_score(const void* logits, int dtype, int B, int64_t row_stride, int vocab,
+                        int true_id, int false_id, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -207,6 +207,23 @@ def gen_bm25_hybrid(ns):
     return len(out["bm25"]) + len(out["hybrid"]) + len(out2["hybrid"])
 
 
+def gen_adjacent_cosine(ns):
+    """Runs the reference's own calculate_cosine_distances (spliter.py:354-372) on seeded sentence
+    embeddings (including a zero row and a duplicated row) and stores inputs + outputs."""
+    from core.file_management.chunker.spliter import calculate_cosine_distances
+    rng = np.random.default_rng(77)
+    emb = rng.standard_normal((40, 96)).astype(np.float32)
+    emb[7] = 0.0                      # zero row: similarity nan -> 0 -> distance 1
+    emb[20] = emb[19]                 # identical neighbours: distance ~0
+    emb[30:] *= 1e-3
+    sentences = [{"sentence": str(i), "combined_sentence_embedding": e.tolist()} for i, e in enumerate(emb)]
+    distances, sentences = calculate_cosine_distances(sentences)
+    assert all(sentences[i]["distance_to_next"] == distances[i] for i in range(len(distances)))
+    np.savez_compressed(os.path.join(GOLD, "adjacent_cosine.npz"), emb=emb,
+                        distances=np.asarray(distances, dtype=np.float64))
+    return len(distances)
+
+
 def main():
     from oracle import ref_loader
     ns = ref_loader.load()
@@ -214,6 +231,7 @@ def main():
     print("rrf cases:", gen_rrf(ns))
     print("dense cases:", gen_dense(ns))
     print("bm25+hybrid cases:", gen_bm25_hybrid(ns))
+    print("adjacent cosine pairs:", gen_adjacent_cosine(ns))
 
 
 if __name__ == "__main__":

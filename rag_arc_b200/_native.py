@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libragarc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu"]
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, F64 = 0, 1, 2, 3
 METRIC_IP, METRIC_COSINE = 0, 1
 POOL_MEAN, POOL_CLS, POOL_LAST = 0, 1, 2
 DENSE_AUTO, DENSE_SIMT, DENSE_TCGEN05 = 0, 1, 2
@@ -29,6 +29,7 @@ EXPORTS = [
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
+    "ragarc_adjacent_cosine_distance", "ragarc_yes_no_score",
     "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
     "ragarc_index_remove", "ragarc_index_ntotal", "ragarc_index_dim", "ragarc_index_rows",
 ]
@@ -86,6 +87,8 @@ def _load():
         "ragarc_merge_topk_keys_p2p": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_bm25_workspace_bytes": (c_size_t, [c_int64, c_int]),
         "ragarc_bm25_scores": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, P, P]),
+        "ragarc_adjacent_cosine_distance": (c_int, [P, c_int, c_int64, c_int, P, P]),
+        "ragarc_yes_no_score": (c_int, [P, c_int, c_int, c_int64, c_int, c_int, c_int, P, P]),
         "ragarc_index_create": (c_int, [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_void_p)]),
         "ragarc_index_free": (c_int, [P]),
         "ragarc_index_reserve": (c_int, [P, c_int64, P]),

@@ -14,6 +14,7 @@ template <> __device__ __forceinline__ float load_f32<float>(const float* p) { r
 template <> __device__ __forceinline__ float load_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 template <> __device__ __forceinline__ float load_f32<__half>(const __half* p) { return __half2float(*p); }
 
+template <typename T> __device__ __forceinline__ float load_f32_round(float v) { T r = from_f32<T>(v); return load_f32(&r); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -297,6 +298,44 @@ __global__ void mmr_select_kernel(const T* __restrict__ X, int d, const T* __res
   }
 }
 
+// ---- adjacent-row cosine distance (SemanticChunker): one warp per pair (i, i+1), fp64 ------------
+template <typename T>
+__global__ void adjacent_cosine_kernel(const T* __restrict__ x, int64_t n, int d, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n - 1) return;
+  const int lane = threadIdx.x & 31;
+  const T* a = x + (size_t)i * d;
+  const T* b = a + d;
+  double dot = 0.0, na = 0.0, nb = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    const double u = (double)a[j], v = (double)b[j];
+    dot = __dadd_rn(dot, __dmul_rn(u, v));
+    na = __dadd_rn(na, __dmul_rn(u, u));
+    nb = __dadd_rn(nb, __dmul_rn(v, v));
+  }
+  dot = warp_sum_f64(dot); na = warp_sum_f64(na); nb = warp_sum_f64(nb);
+  if (lane == 0) {
+    double sim = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb)));
+    if (!isfinite(sim)) sim = 0.0;                     // nan / inf -> 0, as the reference patches them
+    out[i] = __dsub_rn(1.0, sim);
+  }
+}
+
+// ---- reranker tail: P(yes) from the two answer-token logits of the last position ----------------
+// torch: log_softmax over [false, true] in the logits' dtype (fp32 math, result rounded to the
+// dtype), then exp (again rounded to the dtype).
+template <typename T>
+__global__ void yes_no_score_kernel(const T* __restrict__ logits, int B, int64_t row_stride, int true_id,
+                                    int false_id, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float f = load_f32(logits + (size_t)b * row_stride + false_id);
+  const float t = load_f32(logits + (size_t)b * row_stride + true_id);
+  const float m = fmaxf(f, t);
+  const float ls = load_f32_round<T>((t - m) - logf(expf(f - m) + expf(t - m)));   // torch's operation order
+  out[b] = load_f32_round<T>(expf(ls));
+}
+
 }  // namespace ragarc
 
 using namespace ragarc;
@@ -392,6 +431,37 @@ int ragarc_mmr_select(const void* corpus, int64_t n, int d, int dtype, const voi
   else if (dtype == RAGARC_BF16) mmr_select_kernel<__nv_bfloat16><<<nq, 256, smem, st>>>((const __nv_bfloat16*)corpus, d, (const __nv_bfloat16*)queries, cand_rows, fetch_k, k, lambda_mult, out_sel);
   else if (dtype == RAGARC_F16) mmr_select_kernel<__half><<<nq, 256, smem, st>>>((const __half*)corpus, d, (const __half*)queries, cand_rows, fetch_k, k, lambda_mult, out_sel);
   else { set_error("mmr_select: bad dtype %d", dtype); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_adjacent_cosine_distance(const void* x, int dtype, int64_t n, int d, double* out, void* stream) {
+  RA_REQUIRE(n >= 0 && d > 0, "adjacent_cosine_distance: bad shape n=%lld d=%d", (long long)n, d);
+  if (n < 2) return RAGARC_OK;
+  RA_REQUIRE(x && out, "adjacent_cosine_distance: null pointer");
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(n - 1, warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RAGARC_F32) adjacent_cosine_kernel<float><<<grid, warps * 32, 0, st>>>((const float*)x, n, d, out);
+  else if (dtype == RAGARC_F64) adjacent_cosine_kernel<double><<<grid, warps * 32, 0, st>>>((const double*)x, n, d, out);
+  else { set_error("adjacent_cosine_distance: dtype must be RAGARC_F32 or RAGARC_F64"); return RAGARC_ERR_INVALID; }
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_yes_no_score(const void* logits, int dtype, int B, int64_t row_stride, int vocab, int true_id, int false_id,
+                        float* out, void* stream) {
+  RA_REQUIRE(B >= 0 && vocab > 0 && row_stride >= vocab, "yes_no_score: bad shape B=%d vocab=%d stride=%lld", B, vocab,
+             (long long)row_stride);
+  RA_REQUIRE(true_id >= 0 && true_id < vocab && false_id >= 0 && false_id < vocab, "yes_no_score: token id out of range");
+  if (B == 0) return RAGARC_OK;
+  RA_REQUIRE(logits && out, "yes_no_score: null pointer");
+  const unsigned grid = (unsigned)ceil_div(B, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RAGARC_F32) yes_no_score_kernel<float><<<grid, 128, 0, st>>>((const float*)logits, B, row_stride, true_id, false_id, out);
+  else if (dtype == RAGARC_BF16) yes_no_score_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)logits, B, row_stride, true_id, false_id, out);
+  else if (dtype == RAGARC_F16) yes_no_score_kernel<__half><<<grid, 128, 0, st>>>((const __half*)logits, B, row_stride, true_id, false_id, out);
+  else { set_error("yes_no_score: bad dtype %d", dtype); return RAGARC_ERR_INVALID; }
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

@@ -304,3 +304,35 @@ def mmr_select(corpus: torch.Tensor, queries: torch.Tensor, cand_rows: torch.Ten
                                         float(lambda_mult), out.data_ptr(), _stream_ptr(corpus.device)),
                 "mmr_select")
     return out
+
+
+def adjacent_cosine_distance(x: torch.Tensor) -> torch.Tensor:
+    """x: float32 or float64 ``[n,d]`` -> float64 ``[max(n-1,0)]`` cosine distances of consecutive rows
+    (spliter.py:354-372)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise N.RagArcError("x must be a CUDA tensor: rag_arc_b200 has no CPU path")
+    if x.dim() != 2 or x.dtype not in (torch.float32, torch.float64):
+        raise N.RagArcError("adjacent_cosine_distance expects a float32/float64 [n,d] tensor")
+    x = x.contiguous()
+    n, d = x.shape
+    out = torch.empty((max(n - 1, 0),), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib.ragarc_adjacent_cosine_distance(x.data_ptr(), N.F32 if x.dtype == torch.float32 else N.F64, n, d,
+                                                      out.data_ptr(), _stream_ptr(x.device)), "adjacent_cosine_distance")
+    return out
+
+
+def yes_no_score(last_logits: torch.Tensor, true_id: int, false_id: int) -> torch.Tensor:
+    """last_logits: ``[B, vocab]`` (rows may be strided, e.g. ``logits[:, -1, :]``) -> float32 ``[B]``
+    P(yes) as Reranker_Qwen3.py:44-49 computes it."""
+    if not isinstance(last_logits, torch.Tensor) or not last_logits.is_cuda:
+        raise N.RagArcError("last_logits must be a CUDA tensor: rag_arc_b200 has no CPU path")
+    if last_logits.dim() != 2 or last_logits.stride(1) != 1:
+        raise N.RagArcError("yes_no_score expects [B, vocab] with unit stride along the vocabulary")
+    B, V = last_logits.shape
+    out = torch.empty((B,), dtype=torch.float32, device=last_logits.device)
+    with torch.cuda.device(last_logits.device):
+        N.check(N.lib.ragarc_yes_no_score(last_logits.data_ptr(), dtype_code(last_logits.dtype), B,
+                                          last_logits.stride(0) if B > 1 else V, V, int(true_id), int(false_id),
+                                          out.data_ptr(), _stream_ptr(last_logits.device)), "yes_no_score")
+    return out

@@ -193,3 +193,15 @@ def test_comparators_accept_tie_swaps_and_reject_real_errors():
     check_topk([0, 2, 1], [5, 4, 4], [0, 1, 2], [5, 4, 4])
     with pytest.raises(AssertionError):
         check_topk([4, 1, 2], [5, 4, 4], [0, 1, 2], [5, 4, 4])        # wrong id outside any tie group
+
+
+def test_adjacent_cosine_oracle_equals_live_reference_golden():
+    """oracle/chunk.py against the distances the reference's own calculate_cosine_distances
+    (spliter.py:354-372) produced for the committed inputs (oracle/gen_golden.py)."""
+    import os
+    from oracle import chunk
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "adjacent_cosine.npz"))
+    got = chunk.adjacent_cosine_distances(z["emb"])
+    assert np.array_equal(got, z["distances"])
+    assert got[6] == 1.0 and got[7] == 1.0            # neighbours of the zero row
+    assert abs(got[19]) < 1e-12                       # duplicated row
