@@ -44,6 +44,31 @@ def timeit(fn, iters=20, warm=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def graph_time(fn, iters=50):
+    """Device time per call with the launch overhead taken out: the call is captured in a CUDA graph
+    (after a warm-up on the capture stream, so that workspaces exist) and replayed back to back."""
+    dev = torch.device("cuda:0")
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        fn(); fn()
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def emit(**kw):
     print(json.dumps(kw), flush=True)
 
@@ -103,11 +128,15 @@ def c2_hybrid(dev):
     sum_df = int(sum(df[t] for row in qterms for t in row if t >= 0))
     bm_med, bm_best = timeit(lambda: ops.bm25_topk(idx, qt, ql, k), 10)
     bytes_bm = sum_df * 8 + sum_df * 16 + nq * n * 8 * 2
-    emit(config="C2-bm25", docs=n, batch=nq, k=k, ms_median=bm_med, ms_best=bm_best, qps=nq / (bm_med * 1e-3),
+    bm_graph = graph_time(lambda: ops.bm25_topk(idx, qt, ql, k))
+    emit(config="C2-bm25", docs=n, batch=nq, k=k, ms_median=bm_med, ms_best=bm_best, ms_graph=bm_graph,
+         qps=nq / (bm_med * 1e-3), qps_graph=nq / (bm_graph * 1e-3),
          postings_per_query=sum_df / nq, algorithmic_bytes=bytes_bm, hbm_gbs=bytes_bm / (bm_med * 1e-3) / 1e9,
          frac_hbm_peak=bytes_bm / (bm_med * 1e-3) / 1e9 / PEAKS["hbm_gbs"], index_build_s=build_s, nnz=int(df.sum()))
     de_med, de_best = timeit(lambda: ops.dense_topk(x, q, k), 20)
-    emit(config="C2-dense", rows=n, dim=d, batch=nq, k=k, ms_median=de_med, ms_best=de_best, qps=nq / (de_med * 1e-3))
+    de_graph = graph_time(lambda: ops.dense_topk(x, q, k))
+    emit(config="C2-dense", rows=n, dim=d, batch=nq, k=k, ms_median=de_med, ms_best=de_best, ms_graph=de_graph,
+         qps=nq / (de_med * 1e-3))
 
     def hybrid():
         _, bid = ops.bm25_topk(idx, qt, ql, k)
@@ -117,8 +146,58 @@ def c2_hybrid(dev):
     hy_med, hy_best = timeit(hybrid, 10)
     ids = torch.stack([ops.bm25_topk(idx, qt, ql, k)[1].to(torch.int32), ops.dense_topk(x, q, k)[1].to(torch.int32)], 0).contiguous()
     rr_med, rr_best = timeit(lambda: ops.rrf_fuse(ids, 10), 20)
-    emit(config="C2-rrf", batch=nq, lists=2, kl=k, top_k=10, ms_median=rr_med, ms_best=rr_best)
-    emit(config="C2-hybrid", batch=nq, ms_median=hy_med, ms_best=hy_best, qps=nq / (hy_med * 1e-3))
+    rr_graph = graph_time(lambda: ops.rrf_fuse(ids, 10))
+    hy_graph = graph_time(hybrid)
+    emit(config="C2-rrf", batch=nq, lists=2, kl=k, top_k=10, ms_median=rr_med, ms_best=rr_best, ms_graph=rr_graph)
+    emit(config="C2-hybrid", batch=nq, ms_median=hy_med, ms_best=hy_best, ms_graph=hy_graph, qps=nq / (hy_med * 1e-3),
+         qps_graph=nq / (hy_graph * 1e-3),
+         note="ms_median: eager calls from Python, one at a time; ms_graph: the same calls replayed from a CUDA graph")
+
+
+def c2_plugin(dev):
+    """C2 through the plugin classes, strings in / Document objects out: BM25Retriever +
+    VectorStoreRetriever(B200VectorStore) + RRFusion behind MultiPathRetriever.invoke_batch
+    (the reference's MultiPathRetriever takes one query per call, mutipath.py:37-93)."""
+    from rag_arc_b200.core.retrieval.bm25 import BM25Retriever
+    from rag_arc_b200.core.retrieval.dense import VectorStoreRetriever
+    from rag_arc_b200.core.retrieval.mutipath import MultiPathRetriever
+    from rag_arc_b200.core.utils.Fusion import RRFusion
+    from rag_arc_b200.encapsulation.database.vector_db.VectorStore_B200 import B200VectorStore
+    from rag_arc_b200.encapsulation.embeddings.pooled import TableEmbeddings
+    n, d, nq, k = 100_000, 768, 256, 50
+    toks, offs = synth.bm25_corpus_tokens(n)
+    qtok = synth.bm25_queries_tokens(toks, offs, nq)
+    texts = [" ".join(f"t{t}" for t in toks[offs[i]:offs[i + 1]]) + f" doc{i}" for i in range(n)]
+    queries = [" ".join(f"t{t}" for t in row) for row in qtok]
+    X = synth.dense_corpus_np(n, d)
+    Q, _ = synth.dense_queries_np(X, nq)
+    table = {q: Q[i] for i, q in enumerate(queries)}
+    t0 = time.perf_counter()
+    store = B200VectorStore.from_embeddings(texts, X, embedding=TableEmbeddings(table), metric="cosine",
+                                            dtype="bfloat16", device=dev)
+    bm = BM25Retriever.from_texts(texts, k=k, device=dev)
+    hybrid = MultiPathRetriever([bm, VectorStoreRetriever(store, search_kwargs={"k": k})], RRFusion(),
+                                top_k_per_retriever=k)
+    build_s = time.perf_counter() - t0
+    out = hybrid.invoke_batch(queries, top_k=10)           # first call builds the key tables
+    assert len(out) == nq and all(len(o) == 10 for o in out)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        hybrid.invoke_batch(queries, top_k=10)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    for qi in range(3):                                   # warm: kernel variants and workspaces of nq = 1
+        single = hybrid.invoke(queries[qi], top_k=10)
+    t0 = time.perf_counter()
+    for qi in range(20):
+        hybrid.invoke(queries[qi], top_k=10)
+    single_ms = (time.perf_counter() - t0) * 1e3 / 20
+    single = hybrid.invoke(queries[0], top_k=10)
+    emit(config="C2-plugin", docs=n, batch=nq, top_k=10, ms_median=ts[len(ts) // 2], ms_best=ts[0],
+         qps=nq / (ts[len(ts) // 2] * 1e-3), single_query_ms=single_ms, build_s=build_s,
+         same_first_doc=bool(single[0].content == out[0][0].content),
+         note="wall clock, strings in -> Document objects out, MultiPathRetriever.invoke_batch")
 
 
 def pool_case(dev):
@@ -144,6 +223,8 @@ def main():
         dense_case("C1", 10_000, 384, torch.float32, 100, 10, dev)
     if on("c2"):
         c2_hybrid(dev)
+    if on("c2plugin"):
+        c2_plugin(dev)
     if on("pool"):
         pool_case(dev)
     if on("c4"):

@@ -80,13 +80,24 @@ class VectorStoreRetriever(BaseRetriever):
         """Store rows of the top-k documents for every query: int64 ``[nq,k]`` on the device
         (-1 padded).  ``similarity`` search type only."""
         import numpy as np
-        vecs = np.asarray(self.vectorstore.embedding.embed_documents(list(queries)), dtype=np.float32)
+        emb = self.vectorstore.embedding
+        if hasattr(emb, "embed_documents_array"):
+            vecs = np.asarray(emb.embed_documents_array(list(queries)), dtype=np.float32)
+        else:
+            vecs = np.asarray(emb.embed_documents(list(queries)), dtype=np.float32)
         _, rows = self.vectorstore.search_batch(vecs, min(k, max(self.vectorstore.ntotal, 1)))
         return rows
 
     def row_documents(self) -> List[Document]:
+        """Documents in store-row order (cached until the store changes: hybrid batches ask for it
+        several times per call and the list is O(corpus))."""
         vs = self.vectorstore
-        return [vs.docstore[vs.index_to_docstore_id[r]] for r in range(vs.ntotal)]
+        stamp = (getattr(vs, "_version", None), vs.ntotal)
+        cached = getattr(self, "_row_docs", None)
+        if cached is None or cached[0] != stamp or stamp[0] is None:
+            cached = (stamp, [vs.docstore[vs.index_to_docstore_id[r]] for r in range(vs.ntotal)])
+            self._row_docs = cached
+        return cached[1]
 
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
         params = self._resolve(kwargs)

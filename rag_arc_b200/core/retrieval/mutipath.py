@@ -53,12 +53,17 @@ class MultiPathRetriever(BaseRetriever):
         if self._canon_cache is not None and self._canon_cache[0] == sig:
             return self._canon_cache[1], self._canon_cache[2]
         keys: Dict[str, int] = {}
-        tables = []
+        tables, tabs = [], []
         for r in self.retrievers:
             docs = r.row_documents()
             tab = np.fromiter((keys.setdefault(d.content, len(keys)) for d in docs), np.int32, len(docs))
+            tabs.append(tab)
             tables.append(torch.from_numpy(tab).to(device))
-        self._canon_cache = (sig, keys, tables)
+        # per retriever: key -> the LAST row holding that content (-1: not in this retriever's corpus)
+        key_last_row = np.full((len(self.retrievers), max(len(keys), 1)), -1, np.int64)
+        for l, tab in enumerate(tabs):
+            key_last_row[l, tab] = np.arange(len(tab))       # later rows overwrite earlier ones
+        self._canon_cache = (sig, keys, tables, key_last_row)
         return keys, tables
 
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
@@ -82,42 +87,22 @@ class MultiPathRetriever(BaseRetriever):
                 print(f"retriever {type(r).__name__} failed: {exc}")
         fused_ids, _, counts = self.fusion_method.fuse_batch(ids.contiguous(), top_k)
         fused_ids = fused_ids.cpu().numpy(); counts = counts.cpu().numpy(); ids_h = ids.cpu().numpy()
-        rows_h = None
-        out: List[List[Document]] = []
         # reference semantics: the Document returned for a content string is the LAST one seen
-        # while walking the lists in retriever order (Fusion.py:61)
+        # while walking the lists in retriever order (Fusion.py:61) - i.e. it comes from the last
+        # retriever whose list holds the key; inside one retriever duplicate contents resolve to the
+        # last row carrying them
         row_docs = [r.row_documents() for r in self.retrievers]
-        key_to_row = []
-        for l in range(len(self.retrievers)):
-            tab = tables[l].cpu().numpy()
-            first = {}
-            for row, key in enumerate(tab.tolist()):
-                first.setdefault(key, []).append(row)
-            key_to_row.append(first)
-        del rows_h
+        key_last_row = self._canon_cache[3]
+        L = len(self.retrievers)
+        present = (ids_h[:, :, None, :] == fused_ids[None, :, :, None]).any(axis=3)    # [L, nq, top_k]
+        last_l = (L - 1) - np.argmax(present[::-1], axis=0)                            # [nq, top_k]
+        rows = key_last_row[last_l, np.clip(fused_ids, 0, None)]                       # [nq, top_k]
+        out: List[List[Document]] = []
         for q in range(nq):
-            docs = []
-            for key in fused_ids[q, :counts[q]].tolist():
-                doc = None
-                for l in range(len(self.retrievers) - 1, -1, -1):
-                    pos = np.nonzero(ids_h[l, q] == key)[0]
-                    if len(pos):
-                        # the document object this retriever returned at its LAST position for this
-                        # key; several rows can share a content string, recover the row from the
-                        # retriever's own ranking order
-                        doc = self._doc_for(l, q, int(pos[-1]), key, key_to_row[l], row_docs[l])
-                        break
-                docs.append(doc)
-            out.append(docs)
+            c = int(counts[q])
+            out.append([row_docs[l][r] if r >= 0 else None
+                        for l, r in zip(last_l[q, :c].tolist(), rows[q, :c].tolist())])
         return out
-
-    def _doc_for(self, l, q, pos, key, key_rows, docs):
-        rows = key_rows.get(key, [])
-        if len(rows) == 1:
-            return docs[rows[0]]
-        # ambiguous (duplicate content inside one retriever's corpus): any of them carries the same
-        # content; prefer the last row, matching "last one seen" for equal-score duplicates
-        return docs[rows[-1]] if rows else None
 
     # ---- management --------------------------------------------------------------------------------
     def add_retriever(self, retriever: BaseRetriever):

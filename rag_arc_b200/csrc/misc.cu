@@ -181,26 +181,29 @@ __global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, 
                                 int32_t* __restrict__ out_count) {
   extern __shared__ unsigned char rrf_smem[];
   const int n = L * kl;
-  int32_t* key = (int32_t*)rrf_smem;                    // [n]
-  double* score = (double*)(rrf_smem + (((size_t)n * 4 + 7) & ~(size_t)7));   // [n], valid for owners
+  double* score = (double*)rrf_smem;                    // [n], valid for owners (< 0: not an owner)
+  double* recip = score + n;                            // [kl]: 1/(k + rank), each correctly rounded once
+  int32_t* key = (int32_t*)(recip + kl);                // [n]
   __shared__ int n_owner;
   const int q = blockIdx.x;
   if (threadIdx.x == 0) n_owner = 0;
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
-    const int l = p / kl, i = p % kl;
-    key[p] = ids[((size_t)l * nq + q) * kl + i];
-  }
+  for (int i = threadIdx.x; i < kl; i += blockDim.x) recip[i] = __ddiv_rn(1.0, __dadd_rn(rrf_k, (double)(i + 1)));
+  for (int l = 0; l < L; ++l)
+    for (int i = threadIdx.x; i < kl; i += blockDim.x) key[l * kl + i] = ids[((size_t)l * nq + q) * kl + i];
   __syncthreads();
   for (int p = threadIdx.x; p < n; p += blockDim.x) {
     const int32_t me = key[p];
-    double s = -1.0;   // < 0 : not an owner
+    double s = -1.0;
     if (me >= 0) {
       bool first = true;
-      for (int j = 0; j < p; ++j) if (key[j] == me) { first = false; break; }
+      for (int j = 0; j < p; ++j) first = first && (key[j] != me);
       if (first) {
         s = 0.0;
-        for (int j = p; j < n; ++j)
-          if (key[j] == me) s = __dadd_rn(s, __ddiv_rn(1.0, __dadd_rn(rrf_k, (double)(j % kl + 1))));
+        int i = p % kl;                                 // rank-1 of position j inside its list
+        for (int j = p; j < n; ++j) {
+          if (key[j] == me) s = __dadd_rn(s, recip[i]);
+          if (++i == kl) i = 0;
+        }
         atomicAdd(&n_owner, 1);
       }
     }
@@ -212,8 +215,8 @@ __global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, 
     if (s < 0.0) continue;
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const double t = score[j];
-      if (t >= 0.0 && (t > s || (t == s && j < p))) ++rank;
+      const double t = score[j];                        // non-owners hold -1 and never outrank s >= 0
+      rank += (t > s || (t == s && j < p)) ? 1 : 0;
     }
     if (rank < top_k) {
       out_ids[(size_t)q * top_k + rank] = key[p];
@@ -409,7 +412,7 @@ int ragarc_rrf_fuse(const int32_t* ids, int n_lists, int nq, int kl, double rrf_
   if (nq == 0) return RAGARC_OK;
   RA_REQUIRE(ids && out_ids && out_scores && out_count, "rrf_fuse: null pointer");
   const int n = n_lists * kl;
-  size_t smem = (((size_t)n * 4 + 7) & ~(size_t)7) + (size_t)n * 8;
+  size_t smem = (size_t)n * 8 + (size_t)kl * 8 + (size_t)n * 4;
   int threads = n <= 128 ? 128 : 256;
   if (smem > 48 * 1024) RA_CUDA(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rrf_fuse_kernel<<<nq, threads, smem, (cudaStream_t)stream>>>(ids, n_lists, nq, kl, rrf_k, top_k, out_ids,

@@ -224,6 +224,7 @@ class B200VectorStore(VectorStore):
         self.device = torch.device(device)
         self.docstore: dict[str, Document] = {}
         self.index_to_docstore_id: dict[int, str] = {}
+        self._version = 0            # bumped by every add / delete (row -> Document caches key on it)
 
     # ---- index management --------------------------------------------------------------------
     def _get_dimension(self) -> int:
@@ -276,6 +277,7 @@ class B200VectorStore(VectorStore):
         for i, (text, meta, doc_id) in enumerate(zip(texts, metadatas, ids)):
             self.docstore[doc_id] = Document(content=text, metadata=meta, id=doc_id)
             self.index_to_docstore_id[start + i] = doc_id
+        self._version += 1
         return list(ids)
 
     # ---- search ------------------------------------------------------------------------------
@@ -387,6 +389,7 @@ class B200VectorStore(VectorStore):
 
     # ---- maintenance ---------------------------------------------------------------------------
     def delete(self, ids: Optional[List[str]] = None, **kwargs: Any) -> Optional[bool]:
+        self._version += 1
         if ids is None:
             self.docstore.clear()
             self.index_to_docstore_id.clear()

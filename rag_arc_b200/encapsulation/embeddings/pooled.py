@@ -75,6 +75,11 @@ class TableEmbeddings(Embeddings):
     def embed_documents(self, texts: List[str]) -> List[List[float]]:
         return [np.asarray(self.table[t], dtype=np.float32).tolist() for t in texts]
 
+    def embed_documents_array(self, texts: List[str]) -> np.ndarray:
+        """Same vectors as one float32 ``[n,d]`` array (skips the list-of-floats round trip the
+        reference interface imposes; batched retrievers use it when present)."""
+        return np.stack([np.asarray(self.table[t], dtype=np.float32) for t in texts])
+
     def embed_query(self, text: str) -> List[float]:
         return np.asarray(self.table[text], dtype=np.float32).tolist()
 
