@@ -422,7 +422,8 @@ def run_ours(args):
     achieved = flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    # the ncu capture is of the 1-GPU C3 launch; other workloads / shard sizes have no capture -> null
+    if os.path.exists(tpath) and WORKLOAD == "c3" and world == 1 and BATCH == 1024:
         try:
             with open(tpath) as f:
                 traffic = json.load(f).get("dense_tc_kernel_dram_bytes_per_launch")
