@@ -159,6 +159,10 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
     int64_t sr = n / 64;
     if (sr < 64 * (int64_t)k) sr = 64 * (int64_t)k;
     if (sr > 16384) sr = 16384;
+    {
+      static const char* envr = getenv("RAGARC_SEED_ROWS");    // experiments: force the seed sample size
+      if (envr && atoi(envr) > 0 && atoi(envr) <= 262144) sr = atoi(envr);
+    }
     sr = (sr + pl->tile_n - 1) / pl->tile_n * pl->tile_n;
     if (sr / 16 >= 4 * (int64_t)k && n >= 8 * sr) {
       pl->seed_rows = (int)sr;
