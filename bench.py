@@ -355,7 +355,7 @@ def run_ours(args):
     if world == 1:
         pipe = store.pipeline(BATCH, TOPK, depth=2)
         pipe_api = ("B200VectorStore.pipeline(nq,k).submit(pinned host fp32 queries)/result() -> pinned host "
-                    "scores+ids; double-buffered, wall-clock timed")
+                    "scores+ids; per-slot step CUDA-graphed, double-buffered, wall-clock timed")
     elif not args.no_graph:
         from rag_arc_b200.sharded import ShardedSearchPipeline
         ok = 1

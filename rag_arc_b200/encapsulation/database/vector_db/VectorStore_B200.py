@@ -153,27 +153,66 @@ class SearchPipeline:
     """Throughput-oriented batched search over HOST buffers: the host->device copy of batch i+1 and
     the device->host copy of batch i-1 overlap the kernels of batch i (three CUDA streams, `depth`
     staging slots, events between them).  Every batch still pays its own H2D and D2H; only their
-    latency is hidden.
+    latency is hidden.  The kernels of a slot (query normalise + cast, seeding, scoring, merge) are
+    replayed from a CUDA graph, which removes the launch gaps between them.
 
         pipe = store.pipeline(nq=1024, k=100)
         t = pipe.submit(q_host_fp32)          # pinned [nq,d] fp32 tensor (or numpy array)
         scores, rows = pipe.result(t)         # pinned host tensors, valid until the slot is reused
     """
 
-    def __init__(self, index: "FlatIndexB200", nq: int, k: int, depth: int = 2):
+    def __init__(self, index: "FlatIndexB200", nq: int, k: int, depth: int = 2, graph: bool = True):
         self.index, self.nq, self.k, self.depth = index, nq, k, depth
         dev = index.device
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.slots = []
         for _ in range(depth):
             self.slots.append({
-                "q32": torch.empty((nq, index.d), dtype=torch.float32, device=dev),
+                "q32": torch.zeros((nq, index.d), dtype=torch.float32, device=dev),
                 "h_scores": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                 "h_rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
                 "copied_in": torch.cuda.Event(), "computed": torch.cuda.Event(), "copied_out": torch.cuda.Event(),
-                "busy": False,
+                "busy": False, "graph": None,
             })
         self.n_submitted = 0
+        self.use_graph = graph
+        self._captured_for = None
+        if graph:
+            self._capture()
+
+    def _index_state(self):
+        rows = self.index.planes if self.index.x3 else self.index.rows
+        return (rows.data_ptr(), self.index.ntotal)
+
+    def _capture(self) -> None:
+        """One CUDA graph per staging slot: query normalise + cast, seeding, scoring, merge.  The
+        graphs hold the index's row pointer and size, so they are re-captured when the index has
+        grown or shrunk since (checked on every submit)."""
+        dev = self.index.device
+        try:
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for slot in self.slots:                    # workspaces of the capture stream exist now
+                    self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
+                side.synchronize()
+                for slot in self.slots:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        slot["scores"], slot["rows"] = self.index.search_device(
+                            self.index.prepare_queries(slot["q32"]), self.k)
+                    slot["graph"] = g
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._captured_for = self._index_state()
+        except Exception as exc:  # noqa: BLE001 - capture is an optimisation; the eager path is the same work
+            import warnings
+            warnings.warn(f"SearchPipeline: CUDA graph capture failed ({type(exc).__name__}: {exc}); launching eagerly")
+            torch.cuda.synchronize(dev)
+            for slot in self.slots:
+                slot["graph"] = None
+            self.use_graph = False
 
     def submit(self, q_host) -> int:
         ticket = self.n_submitted
@@ -183,6 +222,10 @@ class SearchPipeline:
         qh = torch.as_tensor(q_host)
         if qh.shape != (self.nq, self.index.d) or qh.dtype != torch.float32:
             raise ValueError(f"expected float32 [{self.nq},{self.index.d}] queries")
+        if self.use_graph and self._captured_for != self._index_state():
+            if any(s["busy"] for s in self.slots):
+                raise RuntimeError("the index changed while batches are in flight: collect them first")
+            self._capture()
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(slot["computed"])            # previous use of this slot's q32 is done
             slot["q32"].copy_(qh, non_blocking=True)
@@ -190,13 +233,17 @@ class SearchPipeline:
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(slot["copied_in"])
             self.s_cmp.wait_event(slot["copied_out"])         # previous results of this slot have left
-            slot["scores"], slot["rows"] = self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
+            if slot["graph"] is not None:
+                slot["graph"].replay()
+            else:
+                slot["scores"], slot["rows"] = self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
             slot["computed"].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
             slot["h_scores"].copy_(slot["scores"], non_blocking=True)
             slot["h_rows"].copy_(slot["rows"], non_blocking=True)
-            slot["scores"].record_stream(self.s_out); slot["rows"].record_stream(self.s_out)
+            if slot["graph"] is None:
+                slot["scores"].record_stream(self.s_out); slot["rows"].record_stream(self.s_out)
             slot["copied_out"].record(self.s_out)
         slot["busy"] = True
         self.n_submitted += 1

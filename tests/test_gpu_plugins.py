@@ -20,7 +20,7 @@ from rag_arc_b200.core.retrieval.dense import VectorStoreRetriever
 from rag_arc_b200.core.retrieval.mutipath import MultiPathRetriever
 from rag_arc_b200.core.utils.data_model import Document
 from rag_arc_b200.core.utils.Fusion import RetrievalResult, RRFusion
-from rag_arc_b200.encapsulation.database.vector_db.VectorStore_B200 import B200VectorStore
+from rag_arc_b200.encapsulation.database.vector_db.VectorStore_B200 import B200VectorStore, SearchPipeline
 from rag_arc_b200.encapsulation.embeddings.pooled import B200PooledEmbeddings, HashEmbeddings, TableEmbeddings
 
 pytestmark = pytest.mark.gpu
@@ -112,6 +112,18 @@ def test_search_pipeline_equals_synchronous_search(dev):
         assert torch.equal(r, wr.cpu()) and torch.equal(s, ws.cpu())
     with pytest.raises(ValueError):
         pipe.submit(torch.zeros((3, 64)))
+    assert pipe.use_graph and all(sl["graph"] is not None for sl in pipe.slots)
+    # the index grows (its row matrix is reallocated): the graphs must be re-captured, not replayed stale
+    more = rng.standard_normal((9000, 64)).astype(np.float32)
+    store.add_embeddings([f"u{i}" for i in range(9000)], more)
+    s, r = pipe.result(pipe.submit(batches[0]))
+    ws, wr = store.search_batch(batches[0], 7)
+    assert torch.equal(r, wr.cpu()) and torch.equal(s, ws.cpu())
+    assert int(r.max()) >= 5000                       # rows of the second batch of documents are reachable
+    # eager variant: same results
+    eager = SearchPipeline(store.index, 32, 7, depth=2, graph=False)
+    s2, r2 = eager.result(eager.submit(batches[0]))
+    assert torch.equal(r2, r) and torch.equal(s2, s)
 
 
 def test_float32x3_store_matches_fp32_golden(dev, tmp_path):
