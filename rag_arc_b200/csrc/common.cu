@@ -45,7 +45,7 @@ static int cap_for_k(int k) {
 }
 
 #ifndef RAGARC_DEFAULT_TC_CL
-#define RAGARC_DEFAULT_TC_CL 1
+#define RAGARC_DEFAULT_TC_CL 2
 #endif
 
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* pl, int* path_out) {

@@ -20,7 +20,10 @@
 // 16 consecutive corpus rows (see merge.cu: seed_select_kernel).
 #include <cuda.h>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <new>
+#include <utility>
 #include "common.cuh"
 
 namespace ragarc {
@@ -485,24 +488,28 @@ static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params
   return RAGARC_OK;
 }
 
-// side stream for the launch that runs concurrently with the multicast clusters (one per device)
-struct Side { cudaStream_t stream; cudaEvent_t fork, join; };
-static Side* get_side() {
+// Side stream (+ fork/join events) for the launch that runs concurrently with the multicast
+// clusters: one per (device, caller stream), created on first use and kept - so that a capture in
+// progress on one stream never shares its side stream with eager work on another.
+struct Side { cudaStream_t stream; cudaEvent_t fork, join; std::mutex mu; };
+static Side* get_side(cudaStream_t user) {
   static std::mutex mu;
-  static Side sides[64];
-  static bool made[64] = {};
+  static std::map<std::pair<int, cudaStream_t>, Side*> sides;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lk(mu);
-  if (!made[dev]) {
-    Side s{};
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    sides[dev] = s;
-    made[dev] = true;
+  auto it = sides.find({dev, user});
+  if (it != sides.end()) return it->second;
+  Side* s = new (std::nothrow) Side();
+  if (!s) return nullptr;
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+    delete s;
+    return nullptr;
   }
-  return &sides[dev];
+  sides[{dev, user}] = s;
+  return s;
 }
 
 }  // namespace tc
@@ -590,9 +597,11 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   p.S = pl.S - pl.S_tail;
   p.tiles = pl.tiles_main;
   Side* side = nullptr;
+  std::unique_lock<std::mutex> side_lock;          // the fork/join sequence on the shared side stream is atomic
   if (pl.S_tail > 0) {
-    side = get_side();
+    side = get_side(stream);
     RA_REQUIRE(side != nullptr, "dense tcgen05: cannot create the side stream");
+    side_lock = std::unique_lock<std::mutex>(side->mu);
     RA_CUDA(cudaEventRecord(side->fork, stream));
     RA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }

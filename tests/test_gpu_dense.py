@@ -185,3 +185,27 @@ def test_bf16x3_tensor_core_path_is_fp32_accurate(dev, n, d, nq, k):
     D, I = odense.flat_ip_search(X, Q, k)
     assert np.allclose(scores.cpu().numpy(), D, rtol=1e-5, atol=1e-6)
     assert (ids.cpu().numpy() == I).mean() > 0.999
+
+
+def test_concurrent_host_threads_on_their_own_streams(dev):
+    """The ABI may be entered from arbitrary host threads (the reference runs retrievers in a thread
+    pool, core/retrieval/base.py:82-96): four threads, each on its own CUDA stream, search the same
+    corpus concurrently (512 queries -> the multicast-cluster schedule with its side-stream launch)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n, d, k = 150_000, 128, 20
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=41)
+    qs = [synth.dense_queries_cuda(x, 512, seed=50 + i)[0] for i in range(4)]
+    want = [ops.dense_topk(x, q, k) for q in qs]
+    torch.cuda.synchronize()
+
+    def work(i):
+        st = torch.cuda.Stream(dev)
+        outs = []
+        with torch.cuda.stream(st):
+            for _ in range(6):
+                outs.append(ops.dense_topk(x, qs[i], k))
+        st.synchronize()
+        return all(torch.equal(s, want[i][0]) and torch.equal(r, want[i][1]) for s, r in outs)
+
+    with ThreadPoolExecutor(4) as ex:
+        assert all(ex.map(work, range(4)))

@@ -43,7 +43,7 @@ def test_forced_variants_agree_bitwise(tmp_path):
     import numpy as np
     base = _run(tmp_path, "default", {})
     for name, env in (("cg1", {"RAGARC_TC_CG": "1"}), ("cg2", {"RAGARC_TC_CG": "2"}),
-                      ("cl2", {"RAGARC_TC_CL": "2"}), ("cl4", {"RAGARC_TC_CL": "4"}),
+                      ("cl1", {"RAGARC_TC_CL": "1"}), ("cl2", {"RAGARC_TC_CL": "2"}), ("cl4", {"RAGARC_TC_CL": "4"}),
                       ("slices", {"RAGARC_DENSE_S": "5"}), ("bm25dense", {"RAGARC_BM25_DENSE": "1"})):
         got = _run(tmp_path, name, env)
         for a, b in zip(base, got):
