@@ -16,6 +16,11 @@
 // and append the survivors to the (item,row) candidate list; lists are pruned warp-cooperatively
 // (common.cuh).  The nq x n score matrix never leaves the SM.  While the epilogue drains
 // accumulator b, the MMA warp fills b^1.
+// CL > 1 (CG=2 only): clusters of CL pairs take CL adjacent query blocks over the same corpus tiles;
+// every CTA fetches 1/CL of its corpus half-tile and TMA-multicasts it to the CTAs holding that
+// half in the other pairs (L2->SM corpus traffic / CL).  Such clusters fit on only part of the SMs
+// (GPC boundaries), so launch_dense_tc gives the remaining SMs a concurrent CL=1 launch over the
+// last slices of the corpus.
 // MODE_STORE is the threshold-seeding variant: instead of selecting, it writes the maximum of every
 // 16 consecutive corpus rows (see merge.cu: seed_select_kernel).
 #include <cuda.h>
