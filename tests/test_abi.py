@@ -73,3 +73,21 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_dense_plan_introspection_without_a_gpu():
+    """ragarc_dense_topk_plan is pure host logic: it must answer without a device (148 SMs assumed)
+    and obey its own invariants; unsupported shapes come back as error codes with a message."""
+    from rag_arc_b200 import _native as N
+    p = N.dense_plan(1_000_000, 768, N.BF16, 1024, 100)
+    assert p["path"] == N.DENSE_TCGEN05 and p["rows_per_item"] == 256 and p["query_blocks"] == 4
+    assert p["slices"] * 100 <= 16384 and p["seed_rows"] % 256 == 0 and 0 < p["seed_rows"] <= 16384
+    assert 0 <= p["tail_slices"] < p["slices"] and 0 < p["cluster_tiles"] <= 3907
+    p1 = N.dense_plan(1_000_000, 768, N.BF16, 1, 100)
+    assert p1["rows_per_item"] == 128 and p1["pairs_per_cluster"] == 1 and p1["query_blocks"] == 1
+    pf = N.dense_plan(10_000, 384, N.F32, 100, 10)
+    assert pf["path"] == N.DENSE_SIMT and pf["rows_per_item"] == 64
+    out = (ctypes.c_int * 10)()
+    assert N.lib.ragarc_dense_topk_plan(1000, 64, N.BF16, 4, 5000, 0, out) == 4        # RAGARC_ERR_UNSUPPORTED
+    assert b"2016" in N.lib.ragarc_last_error()
+    assert N.lib.ragarc_dense_topk_plan(1000, 64, N.F32, 4, 5, N.DENSE_TCGEN05, out) == 4

@@ -146,3 +146,32 @@ def test_shard_bounds_cover_rows_exactly_once():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert all(lo <= hi for lo, hi in spans)
+
+
+def test_bm25_doc_range_shards_partition_the_postings_and_keep_global_statistics():
+    """Bm25Index.shard (host side of the multi-GPU BM25): the shards' postings are a partition of the
+    full index's, local doc ids are offset by id_base, idf / vocabulary are the full corpus's."""
+    import numpy as np
+    from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
+    rng = np.random.default_rng(4)
+    words = [f"w{i}" for i in range(30)]
+    corpus = [[words[j] for j in rng.integers(0, 30, rng.integers(0, 9))] for _ in range(57)]
+    full = Bm25Index.from_token_lists(corpus, device=None)
+    assert full.device is None
+    bounds = [(0, 20), (20, 21), (21, 57)]
+    shards = [full.shard(lo, hi, "cpu") for lo, hi in bounds]
+    V = len(full.indptr_np) - 1
+    for t in range(V):
+        docs, tfs, vals = [], [], []
+        for sh in shards:
+            a, b = sh.indptr_np[t], sh.indptr_np[t + 1]
+            docs += (sh.post_doc_np[a:b].astype(np.int64) + sh.id_base).tolist()
+            tfs += sh.post_tf_np[a:b].tolist(); vals += sh.post_val_np[a:b].tolist()
+        a, b = full.indptr_np[t], full.indptr_np[t + 1]
+        assert docs == full.post_doc_np[a:b].tolist() and tfs == full.post_tf_np[a:b].tolist()
+        assert vals == full.post_val_np[a:b].tolist()
+    for sh, (lo, hi) in zip(shards, bounds):
+        assert sh.n_docs == hi - lo and sh.id_base == lo
+        assert sh.idf_np is full.idf_np and sh.vocab is full.vocab and sh.avgdl == full.avgdl
+        assert np.array_equal(sh.doc_norm_np, full.doc_norm_np[lo:hi])
+        assert sh.indptr.dtype == __import__("torch").int64 and sh.post_val.shape[0] == sh.post_doc.shape[0]
