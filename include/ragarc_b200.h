@@ -129,6 +129,27 @@ int ragarc_index_dim(const ragarc_index_t* index);
  * reserve / remove), e.g. as the candidate source of ragarc_mmr_select */
 const void* ragarc_index_rows(const ragarc_index_t* index);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded flat index driven by one host process (the multi-GPU form of the object above; the
+ * reference has no distributed code).  Shard g is a flat index on CUDA device devices[g] (NULL =
+ * devices 0..n_shards-1; a device may appear more than once) holding a contiguous range of global
+ * rows: the first add splits its rows into ceil(n/G)-row ranges, later adds extend the last shard.
+ * A search copies the fp32 host queries to every shard, runs the fused scoring + selection there
+ * concurrently (one stream per shard), gathers the per-shard packed keys (nq*k*8 bytes each) on
+ * shard 0's device and merges them with the same key order as a single index - the result is
+ * identical for any number of shards.  All buffers are HOST memory; calls are synchronous.
+ * (One process per GPU with a collective in between - rag_arc_b200/sharded.py - is the other form:
+ * ragarc_dense_topk_keys per rank, then ragarc_merge_topk_keys[_p2p].)
+ */
+typedef struct ragarc_sharded_index ragarc_sharded_index_t;
+int ragarc_sharded_create(int d, int dtype, int metric, int n_shards, const int* devices,
+                          ragarc_sharded_index_t** out);
+int ragarc_sharded_free(ragarc_sharded_index_t* index);
+int ragarc_sharded_add(ragarc_sharded_index_t* index, const float* rows_host, int64_t n);
+int ragarc_sharded_search(ragarc_sharded_index_t* index, const float* queries_host, int nq, int k,
+                          float* out_scores_host, int64_t* out_ids_host);
+int64_t ragarc_sharded_ntotal(const ragarc_sharded_index_t* index);
+
 /* fp32-accurate search on the tensor cores ("bf16x3").  An fp32 vector v is stored as three bf16
  * planes v1+v2+v3 (v1 = bf16(v), v2 = bf16(v-v1), v3 = bf16(v-v1-v2); exact to 2^-24 relative), a
  * row being [v1 | v2 | v3] (3*d bf16).  The inner product is accumulated in fp32 over the six

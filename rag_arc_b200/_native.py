@@ -32,6 +32,8 @@ EXPORTS = [
     "ragarc_adjacent_cosine_distance", "ragarc_yes_no_score",
     "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
     "ragarc_index_remove", "ragarc_index_ntotal", "ragarc_index_dim", "ragarc_index_rows",
+    "ragarc_sharded_create", "ragarc_sharded_free", "ragarc_sharded_add", "ragarc_sharded_search",
+    "ragarc_sharded_ntotal",
 ]
 
 
@@ -98,6 +100,11 @@ def _load():
         "ragarc_index_ntotal": (c_int64, [P]),
         "ragarc_index_dim": (c_int, [P]),
         "ragarc_index_rows": (ctypes.c_void_p, [P]),
+        "ragarc_sharded_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_void_p)]),
+        "ragarc_sharded_free": (c_int, [P]),
+        "ragarc_sharded_add": (c_int, [P, P, c_int64]),
+        "ragarc_sharded_search": (c_int, [P, P, c_int, c_int, P, P]),
+        "ragarc_sharded_ntotal": (c_int64, [P]),
         "ragarc_bm25_merge_topk": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
         "ragarc_bm25_topk": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
                                      P, c_size_t, P]),

@@ -22,6 +22,22 @@ struct ragarc_index {
   std::mutex mu;
 };
 
+// Row-sharded flat index driven by ONE host process: shard g is a ragarc_index on devices[g] holding
+// a contiguous range of global rows; a search fans the queries out to every shard on its own
+// stream, gathers the per-shard packed keys onto shard 0's device and merges them there.
+struct ragarc_sharded_index {
+  int d = 0, dtype = RAGARC_F32, metric = RAGARC_METRIC_IP;
+  std::vector<ragarc_index*> shard;
+  std::vector<int64_t> base;             // global id of each shard's first row
+  std::vector<cudaStream_t> stream;      // one per shard, on the shard's device
+  std::vector<cudaEvent_t> done;
+  std::vector<void*> keys;               // per shard: [nq,k] packed keys on the shard's device
+  std::vector<size_t> keys_bytes;
+  void* gather = nullptr;                // shard 0's device: [G,nq,k] keys | scores | ids
+  size_t gather_bytes = 0;
+  std::mutex mu;
+};
+
 namespace ragarc {
 
 static size_t esize(int dtype) { return dtype == RAGARC_F32 ? 4 : 2; }
@@ -271,6 +287,189 @@ int ragarc_index_remove(ragarc_index_t* ix, const int64_t* rows_host, int64_t n_
   ix->cap = cap;
   ix->n = n_out;
   return order_end(ix, st);
+}
+
+}  // extern "C"
+
+namespace ragarc {
+
+// per-shard leg of a sharded search: fp32 HOST queries -> this shard's top-k as packed keys carrying
+// global row ids (id_base + local row), written to `keys` (device, [nq,k]); asynchronous on `st`
+static int index_search_keys(ragarc_index* ix, const float* queries_host, int nq, int k, uint64_t id_base,
+                             uint64_t* keys, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  int rc = order_begin(ix, st);
+  if (rc) return rc;
+  if (ix->n == 0) {
+    RA_CUDA(cudaMemsetAsync(keys, 0, (size_t)nq * k * 8, st));     // key 0 = padding
+    return order_end(ix, st);
+  }
+  const size_t q32_bytes = align_up((size_t)nq * ix->d * 4, 256);
+  const size_t qs_bytes = align_up((size_t)nq * ix->d * esize(ix->dtype), 256);
+  rc = grow_buffer(&ix->stage, &ix->stage_bytes, q32_bytes + qs_bytes, st);
+  if (rc) return rc;
+  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->d, ix->dtype, nq, k);
+  RA_REQUIRE(need_ws > 0, "sharded_search: unsupported shape (k=%d)", k);
+  rc = grow_buffer(&ix->ws, &ix->ws_bytes, need_ws, st);
+  if (rc) return rc;
+  float* q32 = (float*)ix->stage;
+  void* qs = (char*)ix->stage + q32_bytes;
+  RA_CUDA(cudaMemcpyAsync(q32, queries_host, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
+  const void* q_use = q32;
+  if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
+    rc = ragarc_normalize_cast(q32, qs, nq, ix->d, ix->dtype, ix->metric == RAGARC_METRIC_COSINE, st);
+    if (rc) return rc;
+    q_use = qs;
+  }
+  rc = ragarc_dense_topk_keys(ix->rows, ix->n, ix->d, ix->dtype, q_use, nq, k, id_base, keys, ix->ws, ix->ws_bytes,
+                              RAGARC_DENSE_AUTO, nullptr, st);
+  if (rc) return rc;
+  return order_end(ix, st);
+}
+
+}  // namespace ragarc
+
+extern "C" {
+
+int ragarc_sharded_create(int d, int dtype, int metric, int n_shards, const int* devices,
+                          ragarc_sharded_index_t** out) {
+  RA_REQUIRE(out != nullptr, "sharded_create: out is NULL");
+  *out = nullptr;
+  RA_REQUIRE(n_shards >= 1 && n_shards <= 64, "sharded_create: n_shards=%d", n_shards);
+  int ndev = 0;
+  RA_CUDA(cudaGetDeviceCount(&ndev));
+  ragarc_sharded_index* sh = new (std::nothrow) ragarc_sharded_index();
+  RA_REQUIRE(sh != nullptr, "sharded_create: out of host memory");
+  sh->d = d; sh->dtype = dtype; sh->metric = metric;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = RAGARC_OK;
+  for (int g = 0; g < n_shards && rc == RAGARC_OK; ++g) {
+    const int dev = devices ? devices[g] : g;
+    if (dev < 0 || dev >= ndev) { set_error("sharded_create: device %d of shard %d does not exist (%d devices)", dev, g, ndev); rc = RAGARC_ERR_INVALID; break; }
+    if (cudaSetDevice(dev) != cudaSuccess) { set_error("sharded_create: cannot select device %d", dev); rc = RAGARC_ERR_CUDA; break; }
+    ragarc_index* ix = nullptr;
+    rc = ragarc_index_create(d, dtype, metric, &ix);
+    if (rc) break;
+    sh->shard.push_back(ix);
+    sh->base.push_back(0);
+    sh->keys.push_back(nullptr);
+    sh->keys_bytes.push_back(0);
+    cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("sharded_create: cannot create stream/event on device %d", dev); rc = RAGARC_ERR_CUDA;
+    }
+    sh->stream.push_back(st);
+    sh->done.push_back(ev);
+  }
+  cudaSetDevice(prev);
+  if (rc) { ragarc_sharded_free(sh); return rc; }
+  *out = sh;
+  return RAGARC_OK;
+}
+
+int ragarc_sharded_free(ragarc_sharded_index_t* sh) {
+  if (!sh) return RAGARC_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (size_t g = 0; g < sh->shard.size(); ++g) {
+    cudaSetDevice(sh->shard[g]->device);
+    cudaDeviceSynchronize();
+    if (g < sh->keys.size() && sh->keys[g]) cudaFree(sh->keys[g]);
+    if (g == 0 && sh->gather) cudaFree(sh->gather);
+    if (g < sh->stream.size() && sh->stream[g]) cudaStreamDestroy(sh->stream[g]);
+    if (g < sh->done.size() && sh->done[g]) cudaEventDestroy(sh->done[g]);
+    ragarc_index_free(sh->shard[g]);
+  }
+  cudaSetDevice(prev);
+  delete sh;
+  return RAGARC_OK;
+}
+
+int64_t ragarc_sharded_ntotal(const ragarc_sharded_index_t* sh) {
+  if (!sh) return -1;
+  int64_t n = 0;
+  for (auto* ix : sh->shard) n += ix->n;
+  return n;
+}
+
+int ragarc_sharded_add(ragarc_sharded_index_t* sh, const float* rows_host, int64_t n) {
+  RA_REQUIRE(sh != nullptr, "sharded_add: null index");
+  RA_REQUIRE(n >= 0, "sharded_add: n=%lld", (long long)n);
+  if (n == 0) return RAGARC_OK;
+  RA_REQUIRE(rows_host != nullptr, "sharded_add: null rows");
+  std::lock_guard<std::mutex> lk(sh->mu);
+  const int G = (int)sh->shard.size();
+  const int64_t total = ragarc_sharded_ntotal(sh);
+  RA_REQUIRE(total + n < (int64_t)0xFFFFFFF0ll, "sharded_add: global row ids must fit 32 bits");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = RAGARC_OK;
+  if (total == 0) {
+    // first load: contiguous ranges of ceil(n/G) rows, shard g = rows [g*per, (g+1)*per)
+    const int64_t per = (n + G - 1) / G;
+    for (int g = 0; g < G && rc == RAGARC_OK; ++g) {
+      const int64_t lo = g * per < n ? g * per : n, hi = (g + 1) * per < n ? (g + 1) * per : n;
+      sh->base[g] = lo;
+      if (hi > lo) {
+        cudaSetDevice(sh->shard[g]->device);
+        rc = ragarc_index_add(sh->shard[g], rows_host + (size_t)lo * sh->d, hi - lo, 1, sh->stream[g]);
+      }
+    }
+  } else {
+    // later rows extend the last shard, whose range stays contiguous (global id = base + local row)
+    ragarc_index* last = sh->shard[G - 1];
+    if (last->n == 0) sh->base[G - 1] = total;
+    cudaSetDevice(last->device);
+    rc = ragarc_index_add(last, rows_host, n, 1, sh->stream[G - 1]);
+  }
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int ragarc_sharded_search(ragarc_sharded_index_t* sh, const float* queries_host, int nq, int k,
+                          float* out_scores_host, int64_t* out_ids_host) {
+  RA_REQUIRE(sh != nullptr, "sharded_search: null index");
+  RA_REQUIRE(nq >= 0 && k > 0, "sharded_search: nq=%d k=%d", nq, k);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(queries_host && out_scores_host && out_ids_host, "sharded_search: null pointer");
+  std::lock_guard<std::mutex> lk(sh->mu);
+  const int G = (int)sh->shard.size();
+  const size_t kb = (size_t)nq * k * 8;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+  // fan out: every shard scores the batch on its own device and stream
+  for (int g = 0; g < G; ++g) {
+    RA_CUDA(cudaSetDevice(sh->shard[g]->device));
+    int rc = grow_buffer(&sh->keys[g], &sh->keys_bytes[g], kb, sh->stream[g]);
+    if (rc) return rc;
+    rc = index_search_keys(sh->shard[g], queries_host, nq, k, (uint64_t)sh->base[g], (uint64_t*)sh->keys[g], sh->stream[g]);
+    if (rc) return rc;
+    RA_CUDA(cudaEventRecord(sh->done[g], sh->stream[g]));
+  }
+  // gather the G key blocks on shard 0's device and merge there (keys order by score, then lowest
+  // global row: the result does not depend on G)
+  const int dev0 = sh->shard[0]->device;
+  cudaStream_t s0 = sh->stream[0];
+  RA_CUDA(cudaSetDevice(dev0));
+  const size_t keys_all = align_up((size_t)G * kb, 256), sc_bytes = align_up((size_t)nq * k * 4, 256);
+  int rc = grow_buffer(&sh->gather, &sh->gather_bytes, keys_all + sc_bytes + (size_t)nq * k * 8, s0);
+  if (rc) return rc;
+  char* gb = (char*)sh->gather;
+  for (int g = 0; g < G; ++g) {
+    RA_CUDA(cudaStreamWaitEvent(s0, sh->done[g], 0));
+    RA_CUDA(cudaMemcpyPeerAsync(gb + (size_t)g * kb, dev0, sh->keys[g], sh->shard[g]->device, kb, s0));
+  }
+  float* d_scores = (float*)(gb + keys_all);
+  int64_t* d_ids = (int64_t*)(gb + keys_all + sc_bytes);
+  rc = ragarc_merge_topk_keys((const uint64_t*)gb, G, nq, k, k, d_scores, d_ids, s0);
+  if (rc) return rc;
+  RA_CUDA(cudaMemcpyAsync(out_scores_host, d_scores, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
+  RA_CUDA(cudaMemcpyAsync(out_ids_host, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s0));
+  RA_CUDA(cudaStreamSynchronize(s0));
+  return RAGARC_OK;
 }
 
 }  // extern "C"

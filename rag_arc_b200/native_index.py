@@ -73,3 +73,52 @@ class NativeFlatIndex:
             self.close()
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
+
+
+class NativeShardedIndex:
+    """``ragarc_sharded_*``: the same index row-sharded over several GPUs (or several shards on one)
+    and driven by this one process - numpy host buffers in and out, results identical to
+    ``NativeFlatIndex`` for any number of shards."""
+
+    def __init__(self, d: int, dtype: str = "float32", metric: str = "cosine", devices=(0,)):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        if metric not in _METRICS:
+            raise ValueError(f"metric must be one of {sorted(_METRICS)} (exact inner product / cosine only)")
+        self.d, self.dtype, self.metric, self.devices = int(d), dtype, metric, tuple(int(x) for x in devices)
+        devs = (ctypes.c_int * len(self.devices))(*self.devices)
+        h = ctypes.c_void_p()
+        N.check(N.lib.ragarc_sharded_create(self.d, _DTYPES[dtype], _METRICS[metric], len(self.devices), devs,
+                                            ctypes.byref(h)), "sharded_create")
+        self._h = h
+
+    @property
+    def ntotal(self) -> int:
+        return int(N.lib.ragarc_sharded_ntotal(self._h))
+
+    def add(self, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"expected [n,{self.d}] float32 rows")
+        N.check(N.lib.ragarc_sharded_add(self._h, x.ctypes.data, x.shape[0]), "sharded_add")
+
+    def search(self, q: np.ndarray, k: int):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise ValueError(f"expected [nq,{self.d}] float32 queries")
+        D = np.empty((q.shape[0], k), np.float32)
+        I = np.empty((q.shape[0], k), np.int64)
+        N.check(N.lib.ragarc_sharded_search(self._h, q.ctypes.data, q.shape[0], int(k), D.ctypes.data, I.ctypes.data),
+                "sharded_search")
+        return D, I
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            N.lib.ragarc_sharded_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

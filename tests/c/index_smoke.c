@@ -94,6 +94,20 @@ int main(void) {
   if (ragarc_index_search(ix, Q, NQ, 5000, Ds, Is, 1, NULL) == RAGARC_OK) { fprintf(stderr, "k=5000 accepted\n"); return 1; }
   if (strlen(ragarc_last_error()) == 0) { fprintf(stderr, "no error message\n"); return 1; }
   CHECK(ragarc_index_free(ix));
+
+  /* the same rows in a three-shard index (all shards on device 0): identical answers */
+  {
+    ragarc_sharded_index_t* sh = NULL;
+    int devs[3] = {0, 0, 0};
+    float Ds2[NQ * K]; int64_t Is2[NQ * K];
+    CHECK(ragarc_sharded_create(D, RAGARC_F32, RAGARC_METRIC_COSINE, 3, devs, &sh));
+    CHECK(ragarc_sharded_add(sh, X, N));
+    if (ragarc_sharded_ntotal(sh) != N) { fprintf(stderr, "sharded ntotal wrong\n"); return 1; }
+    CHECK(ragarc_sharded_search(sh, Q, NQ, K, Ds2, Is2));
+    for (int r = 0; r < N; ++r) { alive[r] = 1; renum[r] = r; }
+    if (brute_check(Xn, alive, Qn, Ds2, Is2, renum)) return 1;
+    CHECK(ragarc_sharded_free(sh));
+  }
   printf("index_smoke: ok (launches so far: %llu)\n", (unsigned long long)ragarc_launch_count());
   free(X); free(Xn); free(alive); free(renum);
   return 0;

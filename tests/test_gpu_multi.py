@@ -146,3 +146,18 @@ def test_sharded_pipeline_host_in_host_out_equals_single_gpu():
         p.join(300)
         assert p.exitcode == 0
     assert out.get() == 1
+
+
+def test_single_process_sharded_index_over_two_gpus():
+    """ragarc_sharded_*: one host process, shards on cuda:0 and cuda:1, numpy host buffers."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import numpy as np
+    from rag_arc_b200 import synth
+    from rag_arc_b200.native_index import NativeFlatIndex, NativeShardedIndex
+    X = synth.dense_corpus_np(50_000, 256, seed=8)
+    Q, planted = synth.dense_queries_np(X, 64, seed=9)
+    flat = NativeFlatIndex(256, "bfloat16", "cosine"); flat.add(X)
+    sh = NativeShardedIndex(256, "bfloat16", "cosine", devices=(0, 1, 1)); sh.add(X)
+    D, I = flat.search(Q, 20); Ds, Is = sh.search(Q, 20)
+    assert np.array_equal(I, Is) and np.array_equal(D, Ds) and (Is[:, 0] == planted).all()

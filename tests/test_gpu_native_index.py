@@ -79,3 +79,32 @@ def test_bad_arguments_fail_loudly(dev):
         ix.remove([9])
     with pytest.raises(ValueError):
         ix.add(np.zeros((4, 32), np.float32))
+
+
+@pytest.mark.parametrize("dtype,metric", [("float32", "ip"), ("bfloat16", "cosine")])
+def test_single_process_sharded_index_equals_flat_index(dev, dtype, metric):
+    """ragarc_sharded_*: three shards (all on device 0 here; tests/test_gpu_multi.py spreads them over
+    two GPUs) must return exactly what one flat index returns - same scores bit for bit, same ids."""
+    from rag_arc_b200.native_index import NativeShardedIndex
+    X = synth.dense_corpus_np(20_001, 128, seed=5) * 2.5
+    Q, _ = synth.dense_queries_np(X, 130, seed=6)
+    flat = NativeFlatIndex(128, dtype, metric); flat.add(X)
+    sh = NativeShardedIndex(128, dtype, metric, devices=(0, 0, 0)); sh.add(X)
+    assert sh.ntotal == flat.ntotal == 20_001
+    for k in (1, 10, 100):
+        D, I = flat.search(Q, k); Ds, Is = sh.search(Q, k)
+        assert np.array_equal(I, Is) and np.array_equal(D.view(np.uint32), Ds.view(np.uint32))
+    # rows added later extend the last shard; a tiny first load leaves shards empty
+    more = synth.dense_corpus_np(500, 128, seed=7) * 2.5
+    flat.add(more); sh.add(more)
+    D, I = flat.search(more[:9], 5); Ds, Is = sh.search(more[:9], 5)
+    assert np.array_equal(I, Is) and np.array_equal(D, Ds) and (I[:, 0] >= 20_001).all()
+    tiny = NativeShardedIndex(128, dtype, metric, devices=(0, 0, 0, 0)); tiny.add(X[:2])
+    ft = NativeFlatIndex(128, dtype, metric); ft.add(X[:2])
+    D, I = ft.search(Q[:3], 4); Ds, Is = tiny.search(Q[:3], 4)
+    assert np.array_equal(I, Is) and (Is[:, 2:] == -1).all() and np.array_equal(D[:, :2], Ds[:, :2])
+    tiny.add(X[2:40]); ft.add(X[2:40])
+    D, I = ft.search(Q[:3], 4); Ds, Is = tiny.search(Q[:3], 4)
+    assert np.array_equal(I, Is) and np.array_equal(D, Ds)
+    for o in (flat, sh, tiny, ft):
+        o.close()
