@@ -128,6 +128,17 @@ class ClockSampler:
                 "window": "timed region" if len(inside) >= 2 else "whole run", "reasons": sorted(reasons)}
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_qps(X32, Q32, k, budget_s=15.0, max_queries=None):
     """The reference's CPU path as it is called: one query at a time,
     normalize_L2 -> IndexFlatIP.search(q[1,d], k) (oracle restatement).  Returns (qps, n_done)."""
@@ -196,7 +207,7 @@ def run_reference(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} queries/step x {args.steps} steps, full corpus, numpy sgemv + exact top-k"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host": {"cpu_count": os.cpu_count(), "torch_threads": cores},
+        "host": {"cpu_count": os.cpu_count(), "torch_threads": cores, "cpu_model": cpu_model()},
     }
     print(json.dumps(line), flush=True)
 
@@ -464,6 +475,7 @@ def run_ours(args):
         cpu = {"value": cqps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{ndone} single-query searches (nq=1, as the reference calls FAISS) over the full "
                          f"1M x 768 fp32 corpus, numpy sgemv + exact top-k; host cpu_count={os.cpu_count()}",
+               "cpu_model": cpu_model(),
                "batched_sgemm_topk_qps": batched_qps,
                "batched_note": "128 queries in one torch-CPU sgemm + topk: an upper bound for a batched CPU "
                                "implementation, not something the reference's API offers"}
