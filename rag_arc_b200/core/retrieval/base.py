@@ -37,5 +37,11 @@ class BaseRetriever(ABC):
             call = functools.partial(self._get_relevant_documents, query, **kwargs)
             return await loop.run_in_executor(pool, call)
 
+    def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
+        """Batched form (B200 addition; the reference takes one query per call).  The default walks
+        the queries one by one; the dense, BM25 and multi-path retrievers override it with one GPU
+        batch."""
+        return [self.invoke(q, **kwargs) for q in queries]
+
     def get_name(self) -> str:
         return type(self).__name__

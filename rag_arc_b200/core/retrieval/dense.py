@@ -81,7 +81,7 @@ class VectorStoreRetriever(BaseRetriever):
         (-1 padded).  ``similarity`` search type only."""
         import numpy as np
         emb = self.vectorstore.embedding
-        if hasattr(emb, "embed_documents_array"):
+        if hasattr(emb, "embed_documents_array"):      # our Embeddings base offers it; foreign plugins may not
             vecs = np.asarray(emb.embed_documents_array(list(queries)), dtype=np.float32)
         else:
             vecs = np.asarray(emb.embed_documents(list(queries)), dtype=np.float32)

@@ -43,6 +43,9 @@ class B200PooledEmbeddings(Embeddings):
             outs.append(ops.pool_normalize(hidden.contiguous(), mask, self.pooling, self.normalize_embeddings))
         return torch.cat(outs, dim=0) if outs else torch.empty((0, 0))
 
+    def embed_documents_array(self, texts: List[str]) -> np.ndarray:
+        return self.embed_documents_tensor(list(texts)).float().cpu().numpy()
+
     def embed_documents(self, texts: List[str]) -> List[List[float]]:
         return self.embed_documents_tensor(texts).cpu().tolist()
 
