@@ -175,3 +175,37 @@ def test_bm25_doc_range_shards_partition_the_postings_and_keep_global_statistics
         assert sh.idf_np is full.idf_np and sh.vocab is full.vocab and sh.avgdl == full.avgdl
         assert np.array_equal(sh.doc_norm_np, full.doc_norm_np[lo:hi])
         assert sh.indptr.dtype == __import__("torch").int64 and sh.post_val.shape[0] == sh.post_doc.shape[0]
+
+
+def test_async_wrappers_and_batch_defaults_of_the_plugin_bases():
+    """base.py:52-67,82-96 / embeddings/base.py:36-61: the async forms run the synchronous methods in
+    a thread pool; invoke_batch / embed_documents_array defaults fall back to the single-item API."""
+    import asyncio
+    import numpy as np
+    from rag_arc_b200.core.file_management.embeddings.base import Embeddings
+    from rag_arc_b200.core.retrieval.base import BaseRetriever
+    from rag_arc_b200.core.utils.data_model import Document
+
+    class E(Embeddings):
+        def embed_documents(self, texts):
+            return [[float(len(t)), 1.0] for t in texts]
+
+        def embed_query(self, text):
+            return [float(len(text)), 2.0]
+
+    class R(BaseRetriever):
+        def _get_relevant_documents(self, query, **kwargs):
+            return [Document(content=query.upper(), metadata={"k": kwargs.get("k")})]
+
+    e, r = E(anything="ignored"), R(search_kwargs={"k": 3}, tags=["t"])
+    assert asyncio.run(e.aembed_documents(["ab", "c"])) == [[2.0, 1.0], [1.0, 1.0]]
+    assert asyncio.run(e.aembed_query("abc")) == [3.0, 2.0]
+    arr = e.embed_documents_array(["ab", "c"])
+    assert arr.dtype == np.float32 and arr.tolist() == [[2.0, 1.0], [1.0, 1.0]]
+    assert r.search_kwargs == {"k": 3} and r.tags == ["t"] and r.get_name() == "R"
+    assert asyncio.run(r.ainvoke("x", k=2))[0].metadata == {"k": 2}
+    assert [d[0].content for d in r.invoke_batch(["a", "b"])] == ["A", "B"]
+    d = Document("text", {"a": 1}, "id1")                      # positional construction, as the reference allows
+    assert Document.from_dict(d.to_dict()) == d and Document("x").metadata == {} and Document("x").id is None
+    with __import__("pytest").raises(TypeError):
+        BaseRetriever()                                        # abstract
