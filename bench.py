@@ -5,17 +5,20 @@
 
 Workload (config.workload = "c3"): exact top-100 over a 1M x 768 bf16 corpus (bge-base shape),
 batch 1024 queries, synthetic normalised embeddings (rag_arc_b200/synth.py).  One "step" = one
-pass of the hot path over one batch.  For N > 1 (launched under torchrun, one rank per GPU) the
-SAME corpus is row-sharded across the ranks, every rank scores the whole batch against its shard,
-the packed (score,id) keys are all-gathered with NCCL and merged on every rank ("strong"
-scaling: total work fixed).
+pass of the hot path over one batch (CUDA-graph replay unless --no-graph).  For N > 1 (launched
+under torchrun, one rank per GPU) the SAME corpus is row-sharded across the ranks, every rank scores
+the whole batch against its shard, and the packed (score,id) keys are exchanged through NVLink peer
+memory fused into the merge kernel, or all-gathered with NCCL ("strong" scaling: total work fixed).
 
-Printed JSON line (rank 0): see the keys below; `value` is device-timed with inputs resident in
-HBM, `e2e.value` goes through the plugin API (`B200VectorStore.search_batch`) with pinned HOST
-queries and host results inside the timed region, `roofline` is the scoring kernel alone (CUDA
-events recorded inside the C ABI around the kernel), `cpu_baseline` is the oracle port of the
-reference's CPU path (single-query FAISS-style calls, as VectorStore_Faiss.py:258-263 makes them)
-timed on this box's host cores on a bounded sample.
+Printed JSON line (rank 0): `value` is device-timed with inputs resident in HBM; `e2e.value` goes
+through the plugin API with pinned HOST queries in and host results out inside the timed region
+(`B200VectorStore.pipeline` at N = 1, `ShardedSearchPipeline` at N > 1; `e2e.sync_ms_per_step` is the
+one-call-per-batch `search_batch` form and `e2e.cabi_host_call_ms` the plain C-ABI
+`ragarc_index_search` with pageable host buffers); `roofline` is the scoring phase alone (CUDA events
+recorded inside the C ABI around it: the multicast-cluster launch plus the concurrent launch on the
+left-over SMs); `config.schedule` is the library's own description of the schedule it used;
+`cpu_baseline` is the oracle port of the reference's CPU path (single-query FAISS-style calls, as
+VectorStore_Faiss.py:258-263 makes them) timed on this box's host cores on a bounded sample.
 """
 from __future__ import annotations
 
