@@ -124,6 +124,12 @@ def gen_dense(ns):
     np.savez_compressed(os.path.join(GOLD, "dense_small.npz"), vecs=vecs, qvecs=qvecs)
     with open(os.path.join(GOLD, "dense_small.json"), "w") as f:
         json.dump(out, f)
+    # a folder as the reference's own FaissVectorStore.save_local leaves it (:432-450): index.faiss
+    # (flat layout, via the faiss shim) + index.pkl holding the REFERENCE's Document objects - the
+    # input of rag_arc_b200.formats / B200VectorStore.load_local
+    store = ns.FaissVectorStore.from_texts(texts[:60], emb, ids=[f"id{i}" for i in range(60)], metric="cosine",
+                                           metadatas=[{"pos": i, "tags": ["a", i % 3]} for i in range(60)])
+    store.save_local(os.path.join(GOLD, "ref_saved_store"), "index")
     return len(out["cases"])
 
 

@@ -5,8 +5,6 @@ executed in a container where FAISS is not installed.  Only the symbols that fil
 (``:2,115-142,153,202,263,381,438,467``) exist; flat indexes only (ivf/hnsw are approximate and
 outside the exact-search scope).
 """
-import pickle
-
 import numpy as np
 
 from oracle.dense import IndexFlatIP, IndexFlatL2, normalize_L2  # noqa: F401
@@ -17,13 +15,33 @@ Index = IndexFlatIP
 
 
 def write_index(index, path):
+    """faiss/impl/index_write.cpp for flat indexes: fourcc, header (d, ntotal, two dummies, is_trained,
+    metric_type), then the row matrix as a size-prefixed block of 4-byte units (restated here
+    independently of the product's reader, rag_arc_b200/formats.py)."""
+    import struct
+    x = np.ascontiguousarray(index._x, dtype="<f4")
+    ip = type(index).__name__ == "IndexFlatIP"
     with open(path, "wb") as f:
-        pickle.dump({"kind": type(index).__name__, "d": index.d, "x": index._x}, f)
+        f.write(b"IxFI" if ip else b"IxF2")
+        f.write(struct.pack("<i", index.d))
+        f.write(struct.pack("<q", x.shape[0]))
+        f.write(struct.pack("<qq", 1 << 20, 1 << 20))
+        f.write(struct.pack("<B", 1))
+        f.write(struct.pack("<i", 0 if ip else 1))
+        f.write(struct.pack("<Q", x.size))
+        f.write(x.tobytes())
 
 
 def read_index(path):
+    import struct
     with open(path, "rb") as f:
-        blob = pickle.load(f)
-    idx = {"IndexFlatIP": IndexFlatIP, "IndexFlatL2": IndexFlatL2}[blob["kind"]](blob["d"])
-    idx.add(blob["x"])
+        blob = f.read()
+    kind = {b"IxFI": IndexFlatIP, b"IxF2": IndexFlatL2}[blob[:4]]
+    d, = struct.unpack_from("<i", blob, 4)
+    n, = struct.unpack_from("<q", blob, 8)
+    off = 4 + 4 + 8 + 16 + 1 + 4
+    count, = struct.unpack_from("<Q", blob, off)
+    assert count == n * d
+    idx = kind(d)
+    idx.add(np.frombuffer(blob, dtype="<f4", count=count, offset=off + 8).reshape(n, d).copy())
     return idx

@@ -493,17 +493,29 @@ class B200VectorStore(VectorStore):
 
     @classmethod
     def load_local(cls, folder_path: str, embeddings, index_name: str = "index", **kwargs: Any) -> "B200VectorStore":
-        with open(os.path.join(folder_path, f"{index_name}.pkl"), "rb") as fh:
-            side = pickle.load(fh)
-        store = cls(embedding=embeddings, index_type=side["index_type"], metric=side["metric"],
-                    normalize_L2=side["normalize_L2"], dtype=side.get("dtype", "float32"), **kwargs)
+        from ....formats import load_reference_sidecar, read_faiss_flat
+        side = load_reference_sidecar(os.path.join(folder_path, f"{index_name}.pkl"))
         path = os.path.join(folder_path, f"{index_name}.b200.npy")
+        faiss_path = os.path.join(folder_path, f"{index_name}.faiss")
+        if os.path.exists(path) and "dtype" in side:
+            kwargs["dtype"] = side["dtype"]          # the row file is in exactly this storage type
+        else:
+            kwargs.setdefault("dtype", "float32")
+        store = cls(embedding=embeddings, index_type=side["index_type"], metric=side["metric"],
+                    normalize_L2=side["normalize_L2"], **kwargs)
         if os.path.exists(path):
             host = torch.from_numpy(np.load(path))
             if store.dtype == torch.bfloat16:
                 host = host.view(torch.bfloat16)
             store.index = store._create_index(int(host.shape[1]))
             store.index.add_prepared(host.to(store.device))
+        elif os.path.exists(faiss_path):
+            # a folder written by the reference's FaissVectorStore.save_local (:432-450): fp32 rows of
+            # a flat index, already normalised by the reference when its metric was cosine (normalising
+            # them again on add is idempotent up to one ulp); `dtype=` chooses the B200 storage type
+            rows, _ = read_faiss_flat(faiss_path)
+            store.index = store._create_index(int(rows.shape[1]))
+            store.index.add(rows)
         store.docstore = side["docstore"]
         store.index_to_docstore_id = side["index_to_docstore_id"]
         return store

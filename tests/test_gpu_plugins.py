@@ -327,3 +327,27 @@ def test_pooled_embeddings_plugin(dev):
     ref = torch.nn.functional.normalize(ref, dim=1).cpu().numpy()
     assert np.allclose(np.array(out), ref, rtol=1e-5, atol=1e-6)
     assert len(emb.embed_query("q")) == 96
+
+
+def test_load_local_imports_a_folder_saved_by_the_reference(dev):
+    """tests/golden/ref_saved_store was written by the reference's FaissVectorStore.save_local
+    (index.faiss + index.pkl with the reference's Document class): B200VectorStore.load_local must
+    serve it - same rows, same documents - in fp32 and, on request, in bf16."""
+    from oracle import dense as odense
+    from rag_arc_b200 import formats
+    folder = os.path.join(GOLD, "ref_saved_store")
+    rows, _ = formats.read_faiss_flat(os.path.join(folder, "index.faiss"))
+    z = np.load(os.path.join(GOLD, "dense_small.npz"))
+    q = z["qvecs"][:6].copy(); odense.normalize_L2(q)
+    D, I = odense.flat_ip_search(rows, q, 5)
+    store = B200VectorStore.load_local(folder, TableEmbeddings({}), device=dev)
+    assert store.ntotal == 60 and store.metric == "cosine" and store.dtype == torch.float32
+    for qi in range(6):
+        res = store.similarity_search_by_vector_with_score(z["qvecs"][qi].tolist(), k=5)
+        assert [d.id for d, _ in res] == [f"id{r}" for r in I[qi]]
+        assert np.allclose([s for _, s in res], D[qi], rtol=1e-5, atol=1e-6)
+        assert res[0][0].metadata["pos"] == int(I[qi][0]) and res[0][0].content.startswith(f"doc {I[qi][0]} ")
+    half = B200VectorStore.load_local(folder, TableEmbeddings({}), device=dev, dtype="bfloat16")
+    assert half.dtype == torch.bfloat16 and half.ntotal == 60
+    res = half.similarity_search_by_vector_with_score(z["qvecs"][0].tolist(), k=1)
+    assert res[0][0].id == f"id{I[0][0]}"
