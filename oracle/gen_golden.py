@@ -172,6 +172,10 @@ def gen_bm25_hybrid(ns):
     texts[40] = texts[12]                    # duplicate content: RRF dedups by content (Fusion.py:59)
     queries = ["w0 w3 w7", "w1 w1 w59", "w5 w40 w41 w42", "nosuchtoken w2", "w58", "w0"]
     bm = make_bm25_retriever(ns, texts, k=5)
+    # the file the reference's own BM25Retriever.save_to_disk writes (bm25.py:550-576): input of
+    # rag_arc_b200.formats.load_reference_bm25_state / BM25Retriever.load_from_disk
+    os.makedirs(os.path.join(GOLD, "ref_saved_bm25"), exist_ok=True)
+    bm.save_to_disk(os.path.join(GOLD, "ref_saved_bm25"))
     out = {"texts": texts, "queries": queries, "bm25": [], "hybrid": []}
     for qi, q in enumerate(queries):
         scores = bm.get_scores(q)

@@ -269,14 +269,25 @@ class BM25Retriever(BaseRetriever):
             raise IOError(f"save failed: {exc}")
 
     @classmethod
-    def load_from_disk(cls, path: str) -> "BM25Retriever":
+    def load_from_disk(cls, path: str, device: str = "cuda") -> "BM25Retriever":
+        """Loads a file written by ``save_to_disk`` - this class's or the REFERENCE's
+        (core/retrieval/bm25.py:550-576).  A reference file carries a ``rank_bm25.BM25Okapi``; its
+        parameters (k1, b, epsilon) are taken over and the CSR index is rebuilt from the documents
+        with the stored tokeniser, which reproduces the reference's idf table bit for bit."""
         if not os.path.exists(path):
             raise IOError(f"file does not exist: {path}")
         try:
-            with open(path, "rb") as fh:
-                st = dill.load(fh)
-            return cls(vectorizer=st["vectorizer"], docs=st["docs"], k=st["k"],
-                       preprocess_func=st["preprocess_func"], bm25_params=st["bm25_params"],
-                       warn_default_preprocess=False)
+            from ...formats import ForeignBM25, load_reference_bm25_state
+            st = load_reference_bm25_state(path)
+            vec = st["vectorizer"]
+            pre = st.get("preprocess_func") or default_preprocessing_func
+            params = dict(st.get("bm25_params") or {})
+            if isinstance(vec, ForeignBM25):
+                for name in ("k1", "b", "epsilon"):
+                    if hasattr(vec, name):
+                        params.setdefault(name, getattr(vec, name))
+                vec = B200BM25Okapi([pre(d.content) for d in st["docs"]], device=device, **params)
+            return cls(vectorizer=vec, docs=st["docs"], k=st["k"], preprocess_func=pre,
+                       bm25_params=st.get("bm25_params") or {}, warn_default_preprocess=False, device=device)
         except Exception as exc:
             raise IOError(f"load failed: {exc}")

@@ -23,6 +23,14 @@ VectorStore_Faiss.py:432-450) leaves two files per store:
 * ``<name>.pkl`` - a pickled dict {docstore, index_to_docstore_id, index_type, metric, normalize_L2}
   whose Documents are instances of the REFERENCE's ``core.utils.data_model.Document``; they are
   re-created here as this package's ``Document`` without importing the reference.
+
+``BM25Retriever.save_to_disk`` (/root/reference core/retrieval/bm25.py:550-576) dill-dumps
+{vectorizer, docs, k, preprocess_func, bm25_params}; ``load_reference_bm25_state`` reads that file
+where neither the reference nor ``rank_bm25`` is importable: the Documents become ours, the
+``rank_bm25.BM25Okapi`` object becomes a plain attribute bag (its parameters and idf table are kept
+for checking; the postings are rebuilt from the documents), the reference's default tokeniser maps
+to ours.  Like the reference's own ``dill.load`` (:596) this trusts the file - a tokeniser pickled by
+value is code.
 """
 from __future__ import annotations
 
@@ -113,3 +121,31 @@ def load_reference_sidecar(path: str) -> Dict[str, Any]:
         if not isinstance(doc, Document):
             raise ValueError(f"{path}: docstore entry {key!r} is not a Document")
     return data
+
+
+class ForeignBM25:
+    """What a pickled ``rank_bm25.BM25Okapi`` turns into here: its attributes (``k1``, ``b``,
+    ``epsilon``, ``corpus_size``, ``avgdl``, ``idf``, ``doc_len``, ``doc_freqs`` ...) without its code."""
+
+
+def load_reference_bm25_state(path: str) -> Dict[str, Any]:
+    """-> {"vectorizer": ForeignBM25 | object, "docs": [Document], "k", "preprocess_func", "bm25_params"}."""
+    import dill
+    from .core.retrieval import bm25 as our_bm25
+
+    mapped = {("rank_bm25", "BM25Okapi"): ForeignBM25,
+              ("core.utils.data_model", "Document"): Document,
+              ("utils.data_model", "Document"): Document,
+              ("core.retrieval.bm25", "default_preprocessing_func"): our_bm25.default_preprocessing_func,
+              ("retrieval.bm25", "default_preprocessing_func"): our_bm25.default_preprocessing_func}
+
+    class _Unpickler(dill.Unpickler):
+        def find_class(self, module, name):
+            hit = mapped.get((module, name))
+            return hit if hit is not None else super().find_class(module, name)
+
+    with open(path, "rb") as f:
+        state = _Unpickler(f).load()
+    if not isinstance(state, dict) or not {"vectorizer", "docs", "k"} <= set(state):
+        raise ValueError(f"{path}: not a BM25 retriever state")
+    return state

@@ -94,3 +94,42 @@ def test_sidecar_loader_refuses_foreign_globals(tmp_path):
     bad.write_bytes(pickle.dumps([1, 2, 3]))
     with pytest.raises(ValueError):
         formats.load_reference_sidecar(str(bad))
+
+
+def test_loads_the_bm25_state_saved_by_the_reference_and_rebuilds_identical_statistics():
+    """tests/golden/ref_saved_bm25/bm25.pkl was dill-dumped by the reference's own
+    BM25Retriever.save_to_disk (its vectorizer is a rank_bm25.BM25Okapi, its docs the reference's
+    Documents).  Loading it here - without the reference or rank_bm25 importable - must rebuild an
+    index whose idf table and average length equal the pickled ones bit for bit."""
+    import json
+    import sys
+    from rag_arc_b200.core.retrieval.bm25 import BM25Retriever
+    path = os.path.join(GOLD, "ref_saved_bm25", "bm25.pkl")
+    assert "rank_bm25" not in sys.modules or "oracle" in (getattr(sys.modules["rank_bm25"], "__file__", "") or "")
+    st = formats.load_reference_bm25_state(path)
+    vec = st["vectorizer"]
+    assert isinstance(vec, formats.ForeignBM25) and st["k"] == 5 and all(type(d) is Document for d in st["docs"])
+    texts = json.load(open(os.path.join(GOLD, "bm25_hybrid_small.json")))["texts"]
+    assert [d.content for d in st["docs"]] == texts and [d.id for d in st["docs"]] == [str(i) for i in range(len(texts))]
+    r = BM25Retriever.load_from_disk(path, device="cpu")
+    ix = r.vectorizer.index
+    assert r.k == 5 and len(r.docs) == len(texts) and ix.n_docs == vec.corpus_size
+    assert ix.avgdl == vec.avgdl and (ix.k1, ix.b, ix.epsilon) == (vec.k1, vec.b, vec.epsilon)
+    ours = {tok: ix.idf_np[ti] for tok, ti in ix.vocab.items()}
+    assert ours.keys() == vec.idf.keys()
+    assert all(np.float64(ours[t]).tobytes() == np.float64(vec.idf[t]).tobytes() for t in ours)
+    assert ix.doc_len_np.tolist() == list(vec.doc_len)
+    with pytest.raises(IOError):
+        BM25Retriever.load_from_disk(os.path.join(GOLD, "nope.pkl"))
+
+
+def test_own_bm25_state_round_trips_through_the_same_loader(tmp_path):
+    from rag_arc_b200.core.retrieval.bm25 import BM25Retriever
+    texts = ["alpha beta gamma", "beta beta delta", "gamma epsilon", "zeta"]
+    r = BM25Retriever.from_texts(texts, ids=["a", "b", "c", "d"], k=2, bm25_params={"k1": 1.2}, device="cpu")
+    r.save_to_disk(str(tmp_path))
+    back = BM25Retriever.load_from_disk(str(tmp_path / "bm25.pkl"), device="cpu")
+    assert back.k == 2 and [d.id for d in back.docs] == ["a", "b", "c", "d"] and back.bm25_params == {"k1": 1.2}
+    a, b = r.vectorizer.index, back.vectorizer.index
+    assert a.k1 == b.k1 == 1.2 and np.array_equal(a.idf_np, b.idf_np) and np.array_equal(a.post_doc_np, b.post_doc_np)
+    assert np.array_equal(a.post_val_np, b.post_val_np) and a.vocab == b.vocab
