@@ -11,12 +11,13 @@
 // Two schedules:
 //  * bm25_range_kernel (the top-k path): a CTA owns (query, range of 24 576 consecutive docs) and
 //    keeps that range's fp64 accumulators in SHARED memory (192 KB).  Posting lists are sorted by
-//    doc, so the range's postings of a term are one contiguous span found by binary search; they are
-//    streamed once (coalesced 4-byte loads of doc and the
-//    per-posting factor), the read-modify-write stays on chip, and
-//    the range's top-k is selected straight out of shared memory.  A small merge kernel combines
-//    the per-range candidates.  HBM/L2 traffic per query = its postings (8 B each) + one 8-byte
-//    doc-norm gather per posting - the algorithmic minimum.
+//    doc, so the range's postings of a term are one contiguous span, found by a warp-cooperative
+//    32-ary search; they are streamed once (coalesced loads of the doc id and the precomputed
+//    per-posting factor, four postings per thread in flight), the read-modify-write stays on chip,
+//    and the range's top-k is selected straight out of shared memory.  A small merge kernel
+//    combines the per-range candidates.  Traffic per query = its postings, 12 B each (16 B with the
+//    doc-norm gather when no factor table is given) - the algorithmic minimum; at C2 the postings
+//    live in L2 and the kernel is issue/latency-bound, not bandwidth-bound (profiles/).
 //  * bm25_score_kernel (ragarc_bm25_scores and the fallback for huge k): one CTA per query with a
 //    dense fp64 accumulator row in global memory (L2), followed by bm25_topk_kernel.
 //
