@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE: oracle-backed, CPU-only stand-ins for the tensor-level entry points of
+``rag_arc_b200.ops`` so that the HOST logic of the plugin classes (bookkeeping, relevance-score maps,
+threshold filters, MMR plumbing, hybrid fusion mapping, persistence) can be exercised against the
+reference's golden vectors on a machine without a GPU.  The kernels themselves are covered by the
+``-m gpu`` tests, which run the very same test bodies against the real library."""
+import contextlib
+
+import numpy as np
+import torch
+
+from oracle import dense as odense
+from oracle import pool as opool
+from oracle import rrf as orrf
+from oracle.bm25 import stable_topk
+
+
+def _normalize_cast(src, dtype=torch.float32, normalize=True, out=None):
+    x = src.detach().cpu().numpy().astype(np.float32).copy()
+    if normalize:
+        odense.normalize_L2(x)
+    res = torch.from_numpy(x).to(dtype)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def _dense_topk(corpus, queries, k, n_rows=None, path=0, return_path=False, **kw):
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    D, I = odense.flat_ip_search(corpus[:n].float().numpy(), queries.float().numpy(), k)
+    res = (torch.from_numpy(D), torch.from_numpy(I))
+    return res + (1,) if return_path else res
+
+
+def _mmr_select(corpus, queries, cand_rows, k, lambda_mult=0.5, *, n_rows=None):
+    """numpy restatement of _mmr_select (VectorStore_Faiss.py:16-62) over the stored rows."""
+    X = corpus.double().numpy(); Q = queries.double().numpy(); C = cand_rows.numpy()
+    out = np.full((C.shape[0], k), -1, np.int32)
+    for qi in range(C.shape[0]):
+        cand = [int(c) for c in C[qi] if c >= 0]
+        remaining = list(range(len(cand)))
+        if not remaining:
+            continue
+        sel = [remaining.pop(0)]
+        while len(sel) < k and remaining:
+            best, best_score = None, None
+            for idx in remaining:
+                qs = float(Q[qi] @ X[cand[idx]])
+                ms = 0.0
+                for s in sel:
+                    ms = max(ms, float(X[cand[s]] @ X[cand[idx]]))
+                score = lambda_mult * qs - (1 - lambda_mult) * ms
+                if best_score is None or score > best_score:
+                    best, best_score = idx, score
+            sel.append(best); remaining.remove(best)
+        out[qi, :len(sel)] = sel
+    return torch.from_numpy(out)
+
+
+def _bm25_scores(index, q_terms, q_len, use_post_val=True):
+    qt, ql = q_terms.numpy(), q_len.numpy()
+    S = np.zeros((qt.shape[0], index.n_docs))
+    for q in range(qt.shape[0]):
+        for t in qt[q, :ql[q]]:
+            if t >= 0:
+                a, b = index.indptr_np[t], index.indptr_np[t + 1]
+                S[q, index.post_doc_np[a:b]] += index.idf_np[t] * index.post_val_np[a:b]
+    return torch.from_numpy(S)
+
+
+def _bm25_topk(index, q_terms, q_len, k, use_post_val=True):
+    S = _bm25_scores(index, q_terms, q_len).numpy()
+    sc = np.full((S.shape[0], k), -np.inf); ids = np.full((S.shape[0], k), -1, np.int64)
+    for q in range(S.shape[0]):
+        top = stable_topk(S[q], min(k, index.n_docs))
+        sc[q, :len(top)] = S[q][top]; ids[q, :len(top)] = top + getattr(index, "id_base", 0)
+    return torch.from_numpy(sc), torch.from_numpy(ids)
+
+
+def _rrf_fuse(ids, top_k, rrf_k=60.0):
+    a = ids.numpy()
+    L, nq, _ = a.shape
+    out_i = np.full((nq, top_k), -1, np.int32); out_s = np.zeros((nq, top_k)); cnt = np.zeros(nq, np.int32)
+    for q in range(nq):
+        keys, scores = orrf.rrf_fuse_ids([a[l, q].tolist() for l in range(L)], top_k, rrf_k)
+        out_i[q, :len(keys)] = keys; out_s[q, :len(keys)] = scores; cnt[q] = len(keys)
+    return torch.from_numpy(out_i), torch.from_numpy(out_s), torch.from_numpy(cnt)
+
+
+def _pool_normalize(x, mask, mode="mean", normalize=True):
+    return torch.from_numpy(opool.pool_normalize(x.float().numpy(), mask.numpy(), mode, normalize).astype(np.float32))
+
+
+@contextlib.contextmanager
+def patched():
+    from rag_arc_b200 import ops
+    fakes = {"normalize_cast": _normalize_cast, "dense_topk": _dense_topk, "mmr_select": _mmr_select,
+             "bm25_scores": _bm25_scores, "bm25_topk": _bm25_topk, "rrf_fuse": _rrf_fuse,
+             "pool_normalize": _pool_normalize}
+    saved = {name: getattr(ops, name) for name in fakes}
+    try:
+        for name, fn in fakes.items():
+            setattr(ops, name, fn)
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
