@@ -83,8 +83,10 @@ def test_faiss_flat_files_round_trip(tmp_path_factory, n, d, metric, seed):
 @SET
 @given(st.integers(1, 50), st.integers(1, 12), st.integers(1, 8), st.integers(0, 2 ** 31 - 1))
 def test_dense_oracle_blocked_search_equals_one_shot(n, d, k, seed):
-    """The oracle's blocked scan + merge (how it handles 1M rows in bounded memory) must equal a
-    single-block scan, including ties (duplicate rows) and k > n padding."""
+    """The oracle's blocked scan + merge (how it handles 1M rows in bounded memory) against a
+    single-block scan, including duplicate rows and k > n padding.  BLAS may round the same dot
+    product differently for different block shapes, so the two are compared the tie-aware way:
+    both must be valid top-k lists of the fp64 scores and agree on the scores to 1e-6."""
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((n, d)).astype(np.float32)
     if n > 3:
@@ -92,6 +94,11 @@ def test_dense_oracle_blocked_search_equals_one_shot(n, d, k, seed):
     Q = rng.standard_normal((3, d)).astype(np.float32)
     D1, I1 = odense.flat_ip_search(X, Q, k, block=7)
     D2, I2 = odense.flat_ip_search(X, Q, k, block=1 << 20)
-    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+    S = Q.astype(np.float64) @ X.astype(np.float64).T
+    kk = min(k, n)
+    for qi in range(3):
+        for D, I in ((D1, I1), (D2, I2)):
+            check_topk_against_scores(I[qi, :kk], D[qi, :kk], S[qi], kk, rtol=1e-5, atol=1e-6)
+    assert np.allclose(D1[:, :kk], D2[:, :kk], rtol=1e-6, atol=1e-6)
     if k > n:
-        assert (I1[:, n:] == -1).all()
+        assert (I1[:, n:] == -1).all() and (I2[:, n:] == -1).all()
