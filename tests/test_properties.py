@@ -13,7 +13,8 @@ from oracle import ref_loader
 from oracle import rrf as orrf
 from oracle.compare import check_topk_against_scores
 
-SET = settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+SET = settings(max_examples=60, deadline=None, derandomize=True, database=None,
+               suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 @SET
