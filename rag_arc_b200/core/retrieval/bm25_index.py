@@ -139,8 +139,11 @@ class Bm25Index:
     # -- queries -------------------------------------------------------------------------------
     def encode_queries(self, queries: Iterable[Sequence[str]]):
         """Token lists -> (q_terms int32 [nq,tmax] with -1 for out-of-vocabulary tokens, q_len)."""
-        rows = [[self.vocab.get(tok, -1) for tok in q] for q in queries]
-        return self._pack(rows)
+        get = self.vocab.get
+        queries = [q if isinstance(q, (list, tuple)) else list(q) for q in queries]
+        lens = np.fromiter((len(q) for q in queries), np.int32, len(queries))
+        flat = np.fromiter((get(tok, -1) for q in queries for tok in q), np.int32, int(lens.sum()))
+        return self._pack_flat(flat, lens)
 
     def encode_query_ids(self, qids: np.ndarray):
         """Integer-token queries for an index built with ``from_token_ids``."""
@@ -151,11 +154,14 @@ class Bm25Index:
         q_len = torch.full((qids.shape[0],), qids.shape[1], dtype=torch.int32, device=self.device)
         return q_terms.contiguous(), q_len
 
+    def _pack_flat(self, flat: np.ndarray, lens: np.ndarray):
+        """Ragged rows given as one flat id array + row lengths -> padded [nq, tmax] (-1) + lengths."""
+        tmax = max(1, int(lens.max()) if lens.size else 1)
+        arr = np.full((lens.shape[0], tmax), -1, np.int32)
+        arr[np.arange(tmax, dtype=np.int32)[None, :] < lens[:, None]] = flat       # row-major fill
+        return (torch.from_numpy(arr).to(self.device), torch.from_numpy(lens.astype(np.int32)).to(self.device))
+
     def _pack(self, rows):
-        tmax = max(1, max((len(r) for r in rows), default=1))
-        arr = np.full((len(rows), tmax), -1, np.int32)
-        ln = np.zeros(len(rows), np.int32)
-        for i, r in enumerate(rows):
-            arr[i, :len(r)] = r
-            ln[i] = len(r)
-        return (torch.from_numpy(arr).to(self.device), torch.from_numpy(ln).to(self.device))
+        lens = np.fromiter((len(r) for r in rows), np.int32, len(rows))
+        flat = np.fromiter((t for r in rows for t in r), np.int32, int(lens.sum()))
+        return self._pack_flat(flat, lens)
