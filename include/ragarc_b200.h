@@ -89,10 +89,13 @@ int ragarc_normalize_cast(const float* src, void* dst, int64_t n, int d, int dst
  */
 size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, int k);
 /* Introspection: the schedule the library would use for this shape (for logs and benchmarks).
- * out[0..10) = path, query rows per work item, CTA pairs per multicast cluster, query blocks,
+ * out[0..16) = path, query rows per work item, CTA pairs per multicast cluster, query blocks,
  * corpus slices, resident work-item slots, seed rows, candidates kept per list, slices given to the
- * concurrent plain-pair launch, corpus tiles given to the multicast-cluster launch. */
-int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out10);
+ * concurrent plain-pair launch, corpus tiles given to the multicast-cluster launch, number of
+ * candidate lists per query that publish an order statistic as a running threshold (0 = threshold
+ * seeding pass instead), which order statistic (m-th best) they publish, and the number of epilogue
+ * warp sets per CTA (= candidate lists per work item and query); the remaining entries are 0. */
+int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out16);
 int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                       int nq, int k, float* out_scores, int64_t* out_ids, void* workspace,
                       size_t workspace_bytes, int path, int* path_used_host, void* stream);
@@ -170,6 +173,18 @@ int ragarc_dense_topk_x3(const void* corpus_planes, int64_t n, int d, const void
 int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                            int nq, int k, uint64_t id_base, uint64_t* out_keys, void* workspace,
                            size_t workspace_bytes, int path, int* path_used_host, void* stream);
+
+/* Same search for the query-owner exchange of the multi-GPU path (rag_arc_b200/sharded.py): the
+ * sorted key row of query q is written straight into the inbox of the rank that owns the query,
+ *   inboxes[q / nq_per_rank] + ((size_t)rank * nq_per_rank + q % nq_per_rank) * k,
+ * where inboxes is a DEVICE array of n_ranks pointers, each to a [n_ranks, nq_per_rank, k] key block
+ * that may live in a peer GPU's memory (stores travel over NVLink inside the merge kernel; the
+ * caller orders them against the owner's ragarc_merge_topk_keys with a device-side barrier).  Every
+ * rank then merges only its own nq_per_rank queries instead of all nq. */
+int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                                int nq, int k, uint64_t id_base, uint64_t* const* inboxes, int n_ranks,
+                                int rank, int nq_per_rank, void* workspace, size_t workspace_bytes,
+                                int path, int* path_used_host, void* stream);
 
 /* k*G-way merge after the NCCL all-gather of ragarc_dense_topk_keys outputs.
  * keys: [nlists, nq, k_in] (as all-gathered, rank-major).  Output as ragarc_dense_topk. */

@@ -12,7 +12,8 @@ import sys
 from ctypes import c_double, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libragarc_b200.so")
+# RAGARC_LIB: load another build of the same library (e.g. one compiled with -DRAGARC_TC_STATS_BUILD)
+LIB_PATH = os.environ.get("RAGARC_LIB") or os.path.join(_HERE, "libragarc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu"]
 
@@ -26,6 +27,7 @@ EXPORTS = [
     "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
     "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk_plan", "ragarc_dense_topk", "ragarc_dense_topk_keys",
+    "ragarc_dense_topk_keys_push",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
@@ -82,6 +84,8 @@ def _load():
                                       c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P,
                                            c_size_t, c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_dense_topk_keys_push": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, c_int,
+                                                c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
         "ragarc_normalize_split3": (c_int, [P, P, c_int64, c_int, c_int, P]),
         "ragarc_dense_topk_x3_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
         "ragarc_dense_topk_x3": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, c_size_t, P]),
@@ -148,10 +152,11 @@ def profile_read():
 
 def dense_plan(n: int, d: int, dtype: int, nq: int, k: int, path: int = 0) -> dict:
     """The schedule ``ragarc_dense_topk`` would use for this shape (needs the current CUDA device)."""
-    out = (ctypes.c_int * 10)()
+    out = (ctypes.c_int * 16)()
     check(lib.ragarc_dense_topk_plan(n, d, dtype, nq, k, path, out), "dense_topk_plan")
     keys = ("path", "rows_per_item", "pairs_per_cluster", "query_blocks", "slices", "resident_items",
-            "seed_rows", "keep", "tail_slices", "cluster_tiles")
+            "seed_rows", "keep", "tail_slices", "cluster_tiles", "publishing_lists", "published_rank",
+            "epilogue_sets")
     return dict(zip(keys, list(out)))
 
 

@@ -146,16 +146,51 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
     if (S > pl->tiles) S = pl->tiles;
   }
   pl->S = (int)S;
-  pl->keep = (int)(merge_cap / S);
+  // Two epilogue warp sets per CTA (tensor-core path), each draining every other tile into its own
+  // candidate list: twice the lists per query, so the merge capacity must hold them, and every slice
+  // needs a few tiles for both sets to have work.  Measured (profiles/r02_epilogue_sets_ab.txt): no
+  // faster than one set - the epilogue is not the pace setter - so it is opt-in: RAGARC_TC_SETS=2.
+  pl->sets = 1;
+  if (tc) {
+    static const char* envs2 = getenv("RAGARC_TC_SETS");
+    const bool want2 = envs2 && envs2[0] == '2' && dense_tc_max_sets() >= 2;
+    const int64_t s_main = S - pl->S_tail;
+    if (want2 && S * 2 * (int64_t)k <= merge_cap && pl->tiles_main >= 4 * s_main &&
+        (pl->S_tail == 0 || pl->tiles - pl->tiles_main >= 4 * (int64_t)pl->S_tail))
+      pl->sets = 2;
+  }
+  pl->keep = (int)(merge_cap / (S * pl->sets));
   if (pl->keep < k) pl->keep = k;
   if (pl->keep > cap - 32) pl->keep = cap - 32;
+  // Published order statistics (tensor-core path, see common.cuh): the lists of the first pub_n
+  // slices - all of them running in the first wave of the main launch - publish their pub_m-th best
+  // score after every tile.  Needs pub_n * pub_m >= k with pub_m <= 8 and at least two tiles per
+  // slice (so that the first tile of every publishing list is a full one).  Replaces the seeding
+  // pass below where it applies; RAGARC_TC_PUB=0 switches it off (A/B measurements).
+  pl->pub_n = 0;
+  pl->pub_m = 0;
+  if (tc) {
+    static const char* envp = getenv("RAGARC_TC_PUB");
+    const bool want = !(envp && envp[0] == '0');
+    const int64_t mbq = pl->MB / cl, s_main = pl->S - pl->S_tail;
+    const int64_t workers = cl > 1 ? dense_tc_units(cg, cl) / cl : dense_tc_units(cg, 1);
+    const int64_t items_main = mbq * s_main;
+    const int64_t units = items_main < workers ? items_main : workers;
+    int64_t pn = units / mbq;                      // slices fully covered by the first wave
+    if (pn > s_main) pn = s_main;
+    if (pn > PUB_LD / pl->sets) pn = PUB_LD / pl->sets;
+    if (want && pn >= 1 && pl->tiles_main >= 2 * pl->sets * s_main) {
+      const int64_t m = ceil_div(k, pn * pl->sets);          // one publishing list per (slice, epilogue set)
+      if (m <= PUB_MAX_M) { pl->pub_n = (int)(pn * pl->sets); pl->pub_m = (int)m; }
+    }
+  }
   // threshold seeding (tensor-core path): the first seed_rows rows are scored, the maximum of every
   // 16-row group is kept, and the k-th largest group maximum - a score that at least k distinct
   // rows reach - becomes the initial shared threshold of each query.  Needs >= 4k groups for a
   // tight bound and is only worth it when the seed rows are a small fraction of the corpus.
   pl->seed_rows = 0;
   pl->seed_S = 0;
-  if (tc && k <= 256) {
+  if (tc && k <= 256 && pl->pub_n == 0) {
     int64_t sr = n / 64;
     if (sr < 64 * (int64_t)k) sr = 64 * (int64_t)k;
     if (sr > 16384) sr = 16384;
@@ -173,9 +208,10 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   }
   size_t items = (size_t)pl->MB * pl->S;
   size_t off = 0;
-  pl->off_lists = off;  off = align_up(off + items * pl->rows_per_item * (size_t)cap * 8, 256);
-  pl->off_counts = off; off = align_up(off + items * pl->rows_per_item * 4, 256);
+  pl->off_lists = off;  off = align_up(off + items * pl->rows_per_item * pl->sets * (size_t)cap * 8, 256);
+  pl->off_counts = off; off = align_up(off + items * pl->rows_per_item * pl->sets * 4, 256);
   pl->off_gthr = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * 4, 256);
+  pl->off_pub = off;    off = align_up(off + (tc ? (size_t)(nq > 0 ? nq : 1) * PUB_LD * 4 : 0), 256);
   pl->off_keys = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * k * 8, 256);
   pl->off_qpad = off;   off = align_up(off + (tc ? (size_t)pl->MB * pl->rows_per_item * d * 2 : 0), 256);
   pl->off_seed = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * (pl->seed_rows / 16) * 4, 256);
@@ -186,7 +222,8 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
 static int dense_common(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
                         int k, uint64_t id_base, uint64_t* out_keys, float* out_scores,
                         int64_t* out_ids, void* workspace, size_t workspace_bytes, int path,
-                        int* path_used_host, cudaStream_t stream, int x3_d = 0) {
+                        int* path_used_host, cudaStream_t stream, int x3_d = 0,
+                        const MergePush* push = nullptr) {
   DensePlan pl;
   pl.x3_d = x3_d;
   int use = 0;
@@ -206,7 +243,10 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   uint32_t* gthr = (uint32_t*)(ws + pl.off_gthr);
   // list lengths are written for every (item,row) by the scoring kernels, so only the shared
   // thresholds need a reset - and not even those when the seed pass overwrites all of them
-  if (!(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0 && n > 0))
+  uint32_t* pub = (uint32_t*)(ws + pl.off_pub);
+  if (use == RAGARC_DENSE_TCGEN05 && pl.pub_n > 0)
+    RA_CUDA(cudaMemsetAsync(gthr, 0, pl.off_keys - pl.off_gthr, stream));   // thresholds + published rungs
+  else if (!(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0 && n > 0))
     RA_CUDA(cudaMemsetAsync(gthr, 0, (size_t)nq * 4, stream));
   if (n == 0) RA_CUDA(cudaMemsetAsync(counts, 0, pl.off_gthr - pl.off_counts, stream));
   ProfRec pr{};
@@ -218,7 +258,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   }
   if (n > 0) {
     if (use == RAGARC_DENSE_TCGEN05)
-      rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr,
+      rc = launch_dense_tc(corpus, n, d, dtype, queries, nq, k, pl, lists, counts, gthr, pub,
                            (float*)(ws + pl.off_seed), ws + pl.off_qpad, prof ? pr.es : nullptr, stream);
     else {
       if (prof) RA_CUDA(cudaEventRecord(pr.es, stream));
@@ -229,7 +269,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
     RA_CUDA(cudaEventRecord(pr.es, stream));
   }
   if (prof) RA_CUDA(cudaEventRecord(pr.e1, stream));
-  rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, out_keys, out_scores, out_ids, stream);
+  rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, out_keys, out_scores, out_ids, push, stream);
   if (rc) return rc;
   if (prof) {
     RA_CUDA(cudaEventRecord(pr.e2, stream));
@@ -304,8 +344,8 @@ size_t ragarc_dense_topk_workspace_bytes(int64_t n, int d, int dtype, int nq, in
   return best;
 }
 
-int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out10) {
-  int* out8 = out10;
+int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path, int* out16) {
+  int* out8 = out16;
   RA_REQUIRE(out8 != nullptr, "dense_topk_plan: out is NULL");
   DensePlan pl;
   int use = 0;
@@ -315,6 +355,7 @@ int ragarc_dense_topk_plan(int64_t n, int d, int dtype, int nq, int k, int path,
   out8[0] = use; out8[1] = pl.rows_per_item; out8[2] = pl.cl; out8[3] = pl.MB; out8[4] = pl.S;
   out8[5] = tc ? dense_tc_units(pl.rows_per_item / 128, pl.cl) : sm_count() * 2;
   out8[6] = pl.seed_rows; out8[7] = pl.keep; out8[8] = pl.S_tail; out8[9] = (int)pl.tiles_main;
+  out8[10] = pl.pub_n; out8[11] = pl.pub_m; out8[12] = pl.sets; out8[13] = out8[14] = out8[15] = 0;
   return RAGARC_OK;
 }
 
@@ -333,6 +374,21 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
   RA_REQUIRE(id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_keys: global ids must fit 32 bits");
   return dense_common(corpus, n, d, dtype, queries, nq, k, id_base, out_keys, nullptr, nullptr,
                       workspace, workspace_bytes, path, path_used_host, (cudaStream_t)stream);
+}
+
+int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,
+                                int nq, int k, uint64_t id_base, uint64_t* const* inboxes, int n_ranks,
+                                int rank, int nq_per_rank, void* workspace, size_t workspace_bytes,
+                                int path, int* path_used_host, void* stream) {
+  RA_REQUIRE(inboxes, "dense_topk_keys_push: null inbox table");
+  RA_REQUIRE(n_ranks > 0 && rank >= 0 && rank < n_ranks && nq_per_rank > 0 &&
+             (int64_t)nq_per_rank * n_ranks >= nq,
+             "dense_topk_keys_push: bad partition n_ranks=%d rank=%d nq_per_rank=%d nq=%d", n_ranks, rank,
+             nq_per_rank, nq);
+  RA_REQUIRE(id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_keys_push: global ids must fit 32 bits");
+  MergePush mp{inboxes, rank, nq_per_rank};
+  return dense_common(corpus, n, d, dtype, queries, nq, k, id_base, nullptr, nullptr, nullptr, workspace,
+                      workspace_bytes, path, path_used_host, (cudaStream_t)stream, 0, &mp);
 }
 
 }  // extern "C"

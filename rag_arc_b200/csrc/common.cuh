@@ -304,6 +304,47 @@ __device__ __forceinline__ void prune_if_needed(RowState& st, int k, int cap, in
   }
 }
 
+// ---- published order statistics ("rungs") ---------------------------------------------------------
+// Every candidate list of the first wave keeps the m best scores it has produced so far in
+// registers and publishes the m-th of them (as an orderable uint32; 0 = fewer than m rows yet) into
+// pub[query][slice].  When all P lists of a query have published, min over them is a score that at
+// least P*m >= k distinct corpus rows reach - a valid (non-strict) global threshold that tightens
+// after every tile, without a separate seeding pass and without waiting for any list to fill up.
+// The publisher itself folds that minimum into the query's shared threshold (atomicMax), so readers
+// keep polling one word per tile; every value ever written is a valid bound, so stale reads of
+// other lists' slots only make the published minimum lag, never wrong.
+constexpr int PUB_LD = 32;      // pub row pitch in words (at most 32 publishing lists per query)
+constexpr int PUB_MAX_M = 8;    // order statistic tracked per list (registers)
+
+__device__ __forceinline__ void top8_insert(float (&t)[PUB_MAX_M], float f) {   // precondition: f > t[7]
+  t[PUB_MAX_M - 1] = f;
+#pragma unroll
+  for (int j = PUB_MAX_M - 1; j > 0; --j)
+    if (t[j] > t[j - 1]) { const float x = t[j]; t[j] = t[j - 1]; t[j - 1] = x; }
+}
+__device__ __forceinline__ float top8_get(const float (&t)[PUB_MAX_M], int idx) {
+  float v = t[0];
+#pragma unroll
+  for (int j = 1; j < PUB_MAX_M; ++j) v = (j == idx) ? t[j] : v;
+  return v;
+}
+// min over the first n published entries of a query's row (0 if any list has not published yet);
+// the row is one 128-byte line, read with eight independent loads
+__device__ __forceinline__ uint32_t pub_min(const uint32_t* row, int n) {
+  uint4 v[PUB_LD / 4];
+#pragma unroll
+  for (int i = 0; i < PUB_LD / 4; ++i) v[i] = __ldcg(reinterpret_cast<const uint4*>(row) + i);
+  uint32_t g = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < PUB_LD / 4; ++i) {
+    g = min(g, 4 * i + 0 < n ? v[i].x : 0xFFFFFFFFu);
+    g = min(g, 4 * i + 1 < n ? v[i].y : 0xFFFFFFFFu);
+    g = min(g, 4 * i + 2 < n ? v[i].z : 0xFFFFFFFFu);
+    g = min(g, 4 * i + 3 < n ? v[i].w : 0xFFFFFFFFu);
+  }
+  return g;
+}
+
 // Workspace plan shared by both dense paths (host side).
 struct DensePlan {
   int rows_per_item;   // query rows per work item (128 tcgen05, 64 simt)
@@ -319,7 +360,9 @@ struct DensePlan {
   int S_tail;          // cl > 1: the last S_tail slices run as plain pairs on the SMs no cluster fits on
   int64_t tiles_main;  // cl > 1: corpus tiles covered by the first S - S_tail slices
   int x3_d;            // >0: rows are three bf16 planes [x1|x2|x3] of a d=x3_d fp32 vector (width 3*x3_d)
-  size_t off_lists, off_counts, off_gthr, off_keys, off_qpad, off_seed, total;
+  int sets;            // tcgen05: epilogue warp sets per CTA (1 or 2) = candidate lists per (item, query row)
+  int pub_n, pub_m;    // tcgen05: pub_n > 0 = the first pub_n slices publish their pub_m-th best score (replaces seeding)
+  size_t off_lists, off_counts, off_gthr, off_pub, off_keys, off_qpad, off_seed, total;
 };
 
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* plan, int* path_out);
@@ -328,18 +371,29 @@ int launch_dense_simt(const void* corpus, int64_t n, int d, int dtype, const voi
                       int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
                       cudaStream_t stream);
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
-                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
+                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr, uint32_t* pub,
                     float* seed_scores, void* qpad, cudaEvent_t after_seed, cudaStream_t stream);
 int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, uint32_t* gthr,
                        cudaStream_t stream);
 bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const void* queries);
 
-// merge of per-slice candidate lists -> sorted keys [nq,k] (+ optional decoded outputs)
+// Multi-GPU "push" exchange: instead of a local [nq,k] block the sorted keys of query q go straight
+// into the inbox of the rank that owns the query (owner = q / nq_per; inboxes[owner] may be peer
+// memory reached over NVLink), at [this rank][q - owner*nq_per][k].
+struct MergePush {
+  uint64_t* const* inboxes;   // device array: one inbox base pointer per rank
+  int rank;                   // this rank (row of the inbox it writes)
+  int nq_per;                 // queries owned by each rank (the last one may own fewer)
+};
+
+// merge of per-slice candidate lists -> sorted keys [nq,k] (+ optional decoded outputs); gthr (may
+// be NULL) = per-query score bound below which candidates are dropped while gathering
 int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
-                       uint64_t id_base, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
-                       cudaStream_t stream);
+                       uint64_t id_base, const uint32_t* gthr, uint64_t* out_keys, float* out_scores,
+                       int64_t* out_ids, const MergePush* push, cudaStream_t stream);
 
 int sm_count();
+int dense_tc_max_sets();              // epilogue warp sets the tcgen05 kernel was built for
 int dense_tc_units(int cg, int cl);   // persistent work-item slots (CTAs or pairs) the tcgen05 kernel keeps resident
 
 }  // namespace ragarc

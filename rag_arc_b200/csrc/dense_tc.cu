@@ -31,16 +31,35 @@
 #include <utility>
 #include "common.cuh"
 
+// experiment counters (appends, prunes, publications, first-tile waits) are compiled in only with
+// -DRAGARC_TC_STATS_BUILD; benchmarks/tc_stats.py reads them
+#ifdef RAGARC_TC_STATS_BUILD
+#define RA_STAT(...) __VA_ARGS__
+#else
+#define RA_STAT(...)
+#endif
+
 namespace ragarc {
+static unsigned long long* g_tc_stats = nullptr;   // RAGARC_TC_STATS=1 counters (experiments)
 namespace tc {
 
 constexpr int BM = 128;            // query rows per CTA (= TMEM lanes)
 constexpr int BN = 256;            // corpus rows per tile (= TMEM columns per accumulator)
 constexpr int BK = 64;             // k elements per stage (= one 128-byte swizzle span)
-constexpr int THREADS = 192;       // warp0 TMA, warp1 MMA/TMEM alloc, warps 2..5 epilogue
+// warp0 TMA, warp1 MMA/TMEM alloc, then one or two SETS of four epilogue warps (one warp per TMEM
+// lane quarter).  With two sets, set e drains accumulator buffer e, i.e. every other corpus tile,
+// into its own candidate lists: two epilogue warps per SM sub-partition hide each other's latencies
+// (a single warp per sub-partition issued only ~20 % of the time and set the pace of the kernel).
+#ifndef RAGARC_TC_MAX_SETS
+#define RAGARC_TC_MAX_SETS 1      // build with -DRAGARC_TC_MAX_SETS=2 to allow RAGARC_TC_SETS=2 (measured: no gain)
+#endif
+constexpr int MAX_SETS = RAGARC_TC_MAX_SETS;
+constexpr int MAX_THREADS = 64 + 128 * MAX_SETS;
 constexpr int TMEM_COLS = 512;
 constexpr int A_BYTES = BM * BK * 2;                       // 16 KB
-constexpr int MISC_BYTES = 256 /*barriers*/ + 4 * 256 * 4 /*hist*/ + 4 * 32 * 32 * 4 /*chunk staging*/;
+// per epilogue warp 4 KB: staging of one 32x32 chunk; the first 1 KB doubles as the prune histogram
+// (a prune only runs after the chunk's survivors have been fetched)
+constexpr int MISC_BYTES = 256 /*barriers*/ + MAX_SETS * 4 * 32 * 32 * 4;
 
 template <int CG> struct Cfg {
   static constexpr int BN_CTA = BN / CG;                   // corpus rows this CTA loads per tile
@@ -162,12 +181,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Pass A of a worker's first tile (see the epilogue): an order statistic of this thread's accumulator
+// row that at least m of its scores reach.  Exact top-m selection over 256 values costs a divergent
+// insertion per element (measured: 20 us per warp); the maxima of the sixteen 16-column groups are
+// scores of sixteen distinct rows, so the m-th largest of THEM is just as valid a rung and needs
+// sixteen insertions.  Kept out of line: it runs once per warp and must not cost the steady-state
+// loop registers.
+struct Top8 { float t[PUB_MAX_M]; };
+static __device__ __noinline__ Top8 first_tile_top8(uint32_t taddr, int nvalid) {
+  Top8 r;
+#pragma unroll
+  for (int j = 0; j < PUB_MAX_M; ++j) r.t[j] = -INFINITY;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    if (c0 >= nvalid) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+    float g0 = -INFINITY, g1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      g0 = fmaxf(g0, (c0 + j < nvalid) ? __uint_as_float(v[j]) : -INFINITY);
+      g1 = fmaxf(g1, (c0 + 16 + j < nvalid) ? __uint_as_float(v[16 + j]) : -INFINITY);
+    }
+    if (g0 > r.t[PUB_MAX_M - 1]) top8_insert(r.t, g0);
+    if (g1 > r.t[PUB_MAX_M - 1]) top8_insert(r.t, g1);
+  }
+  return r;
+}
+
 struct Params {
   int64_t n;       // corpus rows
   int nq, k, num_kb, MB, S;
   int64_t tiles;   // corpus tiles of THIS launch, split into S slices, starting at tile_base
   int64_t tile_base;
-  int slice_base;  // candidate lists are indexed by (slice_base + slice, query block)
+  int slice_base;  // candidate lists are indexed by (slice_base + slice, query block, row, epilogue set)
+  int sets;        // epilogue warp sets per CTA (1 or 2) = candidate lists per (item, row)
   int cap, keep;
   uint32_t idesc;
   uint64_t* lists;
@@ -177,6 +226,15 @@ struct Params {
   int prefetch;        // RAGARC_TC_PREFETCH: L2 prefetch distance in tiles (0 = off; measured 2 % slower when on)
   float* seed_out;     // MODE_STORE: [nq, seed_ld] maxima of 16-row groups of rows [0, n)
   int seed_ld;
+  // published order statistics (common.cuh): pub[query][PUB_LD]; lists of slices < pub_n READ the
+  // minimum of the first pub_n entries as a threshold; lists with list slice < pub_publish also WRITE
+  // their pub_m-th best score (pub_publish = pub_n in the main launch, 0 in the left-over launch)
+  uint32_t* pub;
+  int pub_n, pub_m, pub_publish;
+  int pub_wait_cycles; // a worker's first item waits at most this long for the first-tile rungs of all lists
+  int pub_dbg;         // RAGARC_TC_PUB_DBG (experiments): 1 = no publication after the first tile, 2 = no first-tile exchange, 4 = no rung tracking in the append loop
+  unsigned long long* stats;   // RAGARC_TC_STATS=1 (experiments): appends, prunes, rung publications, first-tile
+                               // wait cycles (sum over warps), first-tile waits that timed out, warps that waited
 };
 
 constexpr int MODE_TOPK = 0, MODE_STORE = 1;
@@ -186,7 +244,7 @@ constexpr int MODE_TOPK = 0, MODE_STORE = 1;
 // multicasts it to the CTAs holding the same half in the other pairs, which divides the corpus
 // operand's L2->SM traffic by CL (the kernel is bound by L2 bandwidth, not by the tensor pipe).
 template <int MODE, int CG, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                 const Params p) {
   using C = Cfg<CG>;
@@ -199,8 +257,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tfull_bar = empty_bar + STAGES;                      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
-  uint32_t* hist = (uint32_t*)(smem + STAGES * STAGE_BYTES + 256);                // [4][256]
-  float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256 + 4 * 256 * 4);   // [4][32][32]
+  float* stage_all = (float*)(smem + STAGES * STAGE_BYTES + 256);   // [epilogue warps][32][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   static_assert(CL == 1 || CG == 2, "multicast clusters are built from CTA pairs");
@@ -311,12 +368,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ------------------------------ epilogue (warps 2..5, every CTA) ----------
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;          // query row inside the CTA == TMEM lane
-    uint32_t* myhist = hist + (warp - 2) * 256;
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;   // this warp drains accumulator buffer `set` when there are two sets
+    const uint32_t two_sets = p.sets > 1 ? 1u : 0u;
+    uint32_t* myhist = (uint32_t*)(stage_all + (warp - 2) * 1024);
     // per-warp staging of one 32x32 chunk: thread `lane` owns row `lane` (128 B); 16-byte chunks are
     // XOR-swizzled by (lane & 7) so that the 128-bit stores of a warp spread over all banks
     float* mystage = stage_all + (warp - 2) * 1024 + lane * 32;
     const int swz = lane & 7;
     uint32_t tcount = 0;
+    bool first_tile_done = false;                 // the first-tile rung exchange happens once per warp
+    RA_STAT(unsigned long long n_app = 0, n_pub = 0, n_prune = 0;)
+    RA_STAT(unsigned long long* tl = p.stats ? p.stats + 16 + ((p.slice_base ? 160 : 0) + blockIdx.x) * 4 : nullptr;)
+    RA_STAT(if (tl && warp == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[0] = g; })
     for (int64_t citem = unit; citem < items; citem += nunits) {
       const int qb = (int)(citem % MBq) * CL + (int)pair;
       const int64_t s = citem / MBq;
@@ -325,14 +388,26 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int irow = (int)rank * BM + row;       // row inside the work item
       const int qrow = qb * ROWS_ITEM + irow;
       RowState st;
-      st.list = p.lists + ((size_t)item * ROWS_ITEM + irow) * (size_t)p.cap;
+      const size_t list_id = ((size_t)item * ROWS_ITEM + irow) * p.sets + set;
+      st.list = p.lists + list_id * (size_t)p.cap;
       st.cnt = 0;
       st.ord_local = 0;
       st.ord_global = 0;
       st.thr = (qrow < p.nq) ? -INFINITY : INFINITY;
       uint32_t* grow = (MODE == MODE_TOPK && qrow < p.nq) ? p.gthr + qrow : nullptr;
+      // published rungs: this row's slot (when its list is one of the publishing ones) and its row of
+      // everybody's rungs
+      const uint32_t* pubrow = (MODE == MODE_TOPK && p.pub_n > 0 && grow) ? p.pub + (size_t)qrow * PUB_LD : nullptr;
+      const int64_t pub_id = (p.slice_base + s) * p.sets + set;                        // this list among the publishing ones
+      const bool publishes = MODE == MODE_TOPK && pub_id < p.pub_publish;              // warp-uniform
+      uint32_t* pubslot = (pubrow && publishes) ? p.pub + (size_t)qrow * PUB_LD + pub_id : nullptr;
+      float top[PUB_MAX_M];
+#pragma unroll
+      for (int j = 0; j < PUB_MAX_M; ++j) top[j] = -INFINITY;
+      float published = -INFINITY;
       for (int64_t t = t0; t < t1; ++t, ++tcount) {
         const uint32_t buf = tcount & 1, aphase = (tcount >> 1) & 1;
+        if (two_sets && buf != set) continue;    // the other set's tile
         if (MODE == MODE_TOPK && grow) {
           uint32_t g = *(volatile uint32_t*)grow;
           if (g > st.ord_global) { st.ord_global = g; st.thr = combine_thr(st.ord_local, g); }
@@ -342,6 +417,44 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(&tfull_bar[buf], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
+        if (MODE == MODE_TOPK && p.pub_n > 0 && citem == unit && !first_tile_done && !(p.pub_dbg & 2)) {
+          first_tile_done = true;
+          // First tile (of this epilogue set) of the worker's first item: nothing is known about the score distribution
+          // yet.  Pass A reads the accumulator once only to find this row's pub_m best scores and
+          // publishes the last of them; then every row waits (bounded: all first-wave workers reach
+          // this point within a few microseconds of each other) until the rungs of all publishing
+          // lists of its query are in, and pass B - the normal loop below, over the same
+          // accumulator - appends only what beats their minimum instead of all 256 rows.
+          if (publishes) {
+            const Top8 a = first_tile_top8(taddr, nvalid);
+            const float pv = top8_get(a.t, p.pub_m - 1);     // pass B re-inserts its survivors into `top`
+            if (pubslot && pv > published) {
+              published = pv;
+              RA_STAT(++n_pub;)
+              __stcg(pubslot, f32_to_ord(pv));
+            }
+          }
+          RA_STAT(if (tl && warp == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[1] = g; })
+          const long long tstart = clock64();
+          uint32_t pg = 0;
+          bool pending = pubrow != nullptr;
+          for (;;) {                                 // both exits are warp-uniform
+            if (pending) { pg = pub_min(pubrow, p.pub_n); pending = pg == 0; }
+            const bool expired = clock64() - tstart > (long long)p.pub_wait_cycles;
+            if (!__any_sync(FULL, pending) || __any_sync(FULL, expired)) break;
+            __nanosleep(100);
+          }
+          if (pg > st.ord_global) {
+            st.ord_global = pg; st.thr = combine_thr(st.ord_local, pg);
+            if (pubslot) atomicMax(grow, pg);        // for the lists that start later and only poll the shared threshold
+          }
+          RA_STAT(if (tl && warp == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); tl[2] = g; })
+          RA_STAT(if (p.stats && lane == 0) {
+            atomicAdd(p.stats + 3, (unsigned long long)(clock64() - tstart));
+            if (pending) atomicAdd(p.stats + 4, 1ull);
+            atomicAdd(p.stats + 5, 1ull);
+          })
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           if (c0 >= nvalid) break;                // warp-uniform
@@ -381,8 +494,30 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             m &= ~(0x80000000u >> j);
             const float f = mystage[(((j >> 2) ^ swz) << 2) | (j & 3)];
             st.list[st.cnt++] = make_key(f, (uint32_t)(r0 + c0 + j));
+            RA_STAT(++n_app;)
+            if (publishes && !(p.pub_dbg & 4) && f > top[PUB_MAX_M - 1]) top8_insert(top, f);
           }
+          RA_STAT(const int before = st.cnt;)
           prune_if_needed(st, p.k, p.cap, p.cap - 32, grow, myhist);
+          RA_STAT(if (st.cnt < before) ++n_prune;)
+        }
+        // Publication schedule: after the 1st, 2nd, 4th, 8th ... tile of the item and after its last
+        // one (the bound ~ m / rows seen, so doubling intervals lose at most a factor of two; the
+        // schedule is warp-uniform, so a warp goes through the sequence a handful of times per item
+        // instead of whenever one of its 32 lists moved).
+        const int64_t ti = t - t0 + 1;
+        if (MODE == MODE_TOPK && publishes && !(p.pub_dbg & 1) && ((ti & (ti - 1)) == 0 || t + 1 + (two_sets ? 1 : 0) >= t1)) {
+          const float pv = top8_get(top, p.pub_m - 1);
+          if (pubslot) {
+            // store this list's rung if it moved, then fold the minimum over all publishing lists of
+            // the query (a score at least pub_n * pub_m >= k rows reach) into the shared threshold
+            if (pv > published) { published = pv; RA_STAT(++n_pub;) __stcg(pubslot, f32_to_ord(pv)); }
+            const uint32_t g = pub_min(pubrow, p.pub_n);
+            if (g > st.ord_global) {
+              atomicMax(grow, g);
+              st.ord_global = g; st.thr = combine_thr(st.ord_local, g);
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -392,12 +527,33 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
       if (MODE == MODE_TOPK) {
+        // A list longer than the merge kernel's per-list budget is first filtered against the best
+        // bound known by now (every thread compacts its own list, no cooperation needed: ~1 us for a
+        // whole warp); only what is still too long afterwards pays for an exact radix prune, which
+        // serialises the lanes of a warp at 3-4 us each.
+        if (grow && st.cnt > p.keep) {
+          uint32_t g = *(volatile uint32_t*)grow;
+          g = g > st.ord_global ? g : st.ord_global;
+          if (g > st.ord_local) {
+            int w = 0;
+            for (int i = 0; i < st.cnt; ++i) {
+              const uint64_t key = st.list[i];
+              if (uint32_t(key >> 32) >= g) st.list[w++] = key;
+            }
+            st.cnt = w;
+          }
+        }
         prune_if_needed(st, p.k, p.cap, p.keep, grow, myhist);
-        p.counts[(size_t)item * ROWS_ITEM + irow] = st.cnt;
+        p.counts[list_id] = st.cnt;
+        RA_STAT(if (p.stats) {
+          atomicAdd(p.stats + 0, n_app); atomicAdd(p.stats + 1, n_prune); atomicAdd(p.stats + 2, n_pub);
+          n_app = 0; n_pub = 0; n_prune = 0;
+        })
       }
     }
   }
 
+  RA_STAT(if (p.stats && warp == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.stats[16 + ((p.slice_base ? 160 : 0) + blockIdx.x) * 4 + 3] = g; })
   tc_fence_before();
   if (CG == 1) __syncthreads(); else cluster_sync_all();   // cluster: nobody leaves while a peer still uses us
   if (warp == 1) {
@@ -453,7 +609,7 @@ static int max_clusters() {
       cudaFuncSetAttribute(dense_tc_kernel<MODE, CG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(sm_count() / (CG * CL) * (CG * CL)));
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(MAX_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -478,7 +634,7 @@ static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params
   constexpr int CG_ = CG * CL;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(units * CG_));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(64 + 128 * (p.sets > 1 ? 2 : 1));
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -519,6 +675,17 @@ static Side* get_side(cudaStream_t user) {
 
 }  // namespace tc
 
+int dense_tc_max_sets() { return tc::MAX_SETS; }
+
+// experiments only (not part of the public header): read and reset the RAGARC_TC_STATS counters
+extern "C" int ragarc_internal_tc_stats(unsigned long long* out2048_host) {
+  if (!g_tc_stats) { for (int i = 0; i < 2048; ++i) out2048_host[i] = 0; return RAGARC_OK; }
+  RA_CUDA(cudaDeviceSynchronize());
+  RA_CUDA(cudaMemcpy(out2048_host, g_tc_stats, 2048 * 8, cudaMemcpyDeviceToHost));
+  RA_CUDA(cudaMemset(g_tc_stats, 0, 2048 * 8));
+  return RAGARC_OK;
+}
+
 int dense_tc_units(int cg, int cl) {
   using namespace tc;
   if (cg == 1) return max_clusters<MODE_TOPK, 1, 1>();
@@ -535,7 +702,7 @@ bool dense_tc_supported(const void* corpus, int64_t n, int d, int dtype, const v
 }
 
 int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq,
-                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr,
+                    int k, const DensePlan& pl, uint64_t* lists, int* counts, uint32_t* gthr, uint32_t* pub,
                     float* seed_scores, void* qpad, cudaEvent_t after_seed, cudaStream_t stream) {
   using namespace tc;
   RA_REQUIRE(dense_tc_supported(corpus, n, d, dtype, queries),
@@ -568,6 +735,24 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   p.num_kb = pl.x3_d > 0 ? 6 * p.kb_per_plane : (d + BK - 1) / BK;
   p.tiles = pl.tiles; p.tile_base = 0; p.slice_base = 0; p.cap = pl.cap; p.keep = pl.keep; p.lists = lists; p.counts = counts; p.gthr = gthr;
   p.seed_out = nullptr; p.seed_ld = 0;
+  p.sets = pl.sets;
+  p.pub = pub; p.pub_n = pl.pub_n; p.pub_m = pl.pub_m; p.pub_publish = pl.pub_n;
+  {
+    static const char* envd = getenv("RAGARC_TC_PUB_DBG");
+    p.pub_dbg = envd ? atoi(envd) : 0;
+  }
+  p.stats = nullptr;
+  {
+    static const char* envst = getenv("RAGARC_TC_STATS");
+    if (envst && envst[0] == '1') {
+      if (!g_tc_stats) { RA_CUDA(cudaMalloc(&g_tc_stats, 2048 * sizeof(unsigned long long))); RA_CUDA(cudaMemset(g_tc_stats, 0, 2048 * 8)); }
+      p.stats = g_tc_stats;
+    }
+  }
+  {
+    static const char* envw = getenv("RAGARC_TC_PUB_WAIT");      // experiments: first-tile wait bound in cycles
+    p.pub_wait_cycles = envw ? atoi(envw) : 40000;
+  }
   {
     static const char* env = getenv("RAGARC_TC_PREFETCH");
     p.prefetch = env ? atoi(env) : 0;
@@ -579,6 +764,7 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   if (pl.seed_rows > 0) {
     // seed pass over the first seed_rows rows -> group maxima -> k-th largest per query -> gthr
     Params ps = p;
+    ps.pub_n = 0; ps.pub_publish = 0;
     CUtensorMap mxs;
     rc = make_map(&mxs, corpus, pl.seed_rows, d, dtype, BN / cg);
     if (rc) return rc;
@@ -621,6 +807,7 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
     pt.tiles = pl.tiles - pl.tiles_main;
     pt.tile_base = pl.tiles_main;
     pt.slice_base = pl.S - pl.S_tail;
+    pt.pub_publish = 0;                          // the left-over pairs read the rungs but publish none
     rc = launch_one<MODE_TOPK, 2, 1>(mq, mxt, pt, side->stream);
     if (rc) return rc;
     RA_CUDA(cudaEventRecord(side->join, side->stream));

@@ -109,6 +109,7 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P) {
   __syncthreads();
 }
 
+// out_keys / out_scores / out_ids point at the [nq,k] blocks; the row of query q is written.
 __device__ __forceinline__ void emit_topk(const uint64_t* s, int q, int k, uint64_t id_base,
                                           uint64_t* out_keys, float* out_scores, int64_t* out_ids) {
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -122,6 +123,8 @@ __device__ __forceinline__ void emit_topk(const uint64_t* s, int q, int k, uint6
     if (out_ids) out_ids[(size_t)q * k + j] = key ? (int64_t)(key_row(key) + id_base) : -1;
   }
 }
+
+
 
 // Shared tail: keys[0..T) gathered in smem -> top-k sorted in win[0..PK) -> outputs.
 __device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, int PK, uint64_t* win,
@@ -154,9 +157,10 @@ __device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, i
 constexpr int MERGE_WIN = 512;       // survivors that are sorted directly
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S,
-                   int rows, int cap, int k, int PK, int tmax, uint64_t id_base, uint64_t* out_keys,
-                   float* out_scores, int64_t* out_ids) {
+merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S, int sets,
+                   int rows, int cap, int k, int PK, int tmax, uint64_t id_base,
+                   const uint32_t* __restrict__ gthr, uint64_t* out_keys,
+                   float* out_scores, int64_t* out_ids, MergePush push) {
   extern __shared__ uint64_t msm[];
   uint64_t* keys = msm;                       // [tmax]
   uint64_t* win = msm + tmax;                 // [max(PK, MERGE_WIN)] survivors / winners
@@ -175,7 +179,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     for (int s0 = 0; s0 < S; s0 += 32) {
       const int s = s0 + lane;
       int c = 0;
-      if (s < S) c = counts[((size_t)s * MB + qb) * rows + r];
+      if (s < S) c = counts[(((size_t)(s / sets) * MB + qb) * rows + r) * sets + (s % sets)];
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -188,36 +192,45 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     if (lane == 0) { offs[S] = carry; nwin = 0; omin = 0xFFFFFFFFu; omax = 0u; }
   }
   __syncthreads();
-  int total = offs[S];
-  if (total > tmax) total = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
-  // (A) gather, one warp per list (round robin), up to 8 independent 32-key chunk loads in flight
+  int total_raw = offs[S];
+  if (total_raw > tmax) total_raw = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
+  // (A) flattened gather: element e of the concatenated lists belongs to the list found by binary
+  // search in the prefix sums, so every load is independent of every other (a warp-per-list loop
+  // serialises S/16 dependent L2 round trips).  Candidates below the query's shared threshold - a
+  // score that at least k rows are known to reach - are dropped on the way in.
   {
+    const uint32_t bound = gthr ? gthr[q] : 0u;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
-    for (int sl = warp; sl < S; sl += nwarp) {
-      const int o = offs[sl];
-      int c = offs[sl + 1] - o;
-      if (o + c > tmax) c = tmax - o > 0 ? tmax - o : 0;
-      const uint64_t* src = lists + (((size_t)sl * MB + qb) * rows + r) * (size_t)cap;
-      for (int j0 = 0; j0 < c; j0 += 256) {
-        uint64_t v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = j0 + u * 32 + lane;
-          v[u] = j < c ? src[j] : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = j0 + u * 32 + lane;
-          if (j < c) {
-            keys[o + j] = v[u];
-            const uint32_t hi = uint32_t(v[u] >> 32);
-            lmin = min(lmin, hi); lmax = max(lmax, hi);
-          }
-        }
+    for (int b = 0; b < total_raw; b += blockDim.x) {
+      const int e = b + threadIdx.x;
+      uint64_t key = 0ull;
+      if (e < total_raw) {
+        int lo = 0, hi = S;                   // largest sl with offs[sl] <= e
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= e) lo = mid; else hi = mid; }
+        key = lists[((((size_t)(lo / sets) * MB + qb) * rows + r) * sets + (lo % sets)) * (size_t)cap + (e - offs[lo])];
+      }
+      const uint32_t ord = uint32_t(key >> 32);
+      const bool keep = e < total_raw && ord >= bound;
+      const unsigned bal = __ballot_sync(FULL, keep);
+      uint32_t base = 0;
+      if (lane == 0 && bal) base = atomicAdd(&nwin, (uint32_t)__popc(bal));
+      base = __shfl_sync(FULL, base, 0);
+      if (keep) {
+        keys[base + __popc(bal & ((1u << lane) - 1u))] = key;
+        lmin = min(lmin, ord); lmax = max(lmax, ord);
       }
     }
     lmin = __reduce_min_sync(FULL, lmin); lmax = __reduce_max_sync(FULL, lmax);
     if (lane == 0) { atomicMin(&omin, lmin); atomicMax(&omax, lmax); }
+  }
+  __syncthreads();
+  const int total = (int)nwin;
+  __syncthreads();
+  if (threadIdx.x == 0) nwin = 0;
+  if (push.inboxes) {
+    // redirect the key output of this query to its owner's inbox (see MergePush)
+    const int owner = q / push.nq_per;
+    out_keys = push.inboxes[owner] + (ptrdiff_t)(push.rank - owner) * (ptrdiff_t)push.nq_per * (ptrdiff_t)k;
   }
   __syncthreads();
   bool fast = total > k;
@@ -387,17 +400,20 @@ seed_select_kernel(const float* __restrict__ scores, int S, int k, uint32_t* __r
 static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
-                       uint64_t id_base, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
-                       cudaStream_t stream) {
-  const int tmax = pl.S * pl.keep;
+                       uint64_t id_base, const uint32_t* gthr, uint64_t* out_keys, float* out_scores,
+                       int64_t* out_ids, const MergePush* push, cudaStream_t stream) {
+  const int VS = pl.S * pl.sets;              // candidate lists per query
+  const int tmax = VS * pl.keep;
   const int PK = next_pow2(k);
-  RA_REQUIRE(tmax <= 16384 && pl.S <= 1024 && PK <= 2048, "merge: S*keep=%d too large", tmax);
-  const size_t smem = (size_t)(tmax + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(pl.S + 1) * 4;
+  RA_REQUIRE(tmax <= 16384 && VS <= 1024 && PK <= 2048, "merge: S*sets*keep=%d too large", tmax);
+  const size_t smem = (size_t)(tmax + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(VS + 1) * 4;
   RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (16384 + 2048) * 8 + 1025 * 4));
-  merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, pl.S, pl.rows_per_item,
-                                                         pl.cap, k, PK, tmax, id_base, out_keys, out_scores,
-                                                         out_ids);
+  MergePush mp{nullptr, 0, 1};
+  if (push) mp = *push;
+  merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, VS, pl.sets, pl.rows_per_item,
+                                                         pl.cap, k, PK, tmax, id_base, gthr, out_keys, out_scores,
+                                                         out_ids, mp);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

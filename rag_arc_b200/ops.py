@@ -166,6 +166,26 @@ def dense_topk_keys(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base
     return keys
 
 
+def dense_topk_keys_push(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base: int,
+                         inbox_table: torch.Tensor, rank: int, nq_per_rank: int, *,
+                         n_rows: Optional[int] = None, path: int = N.DENSE_AUTO) -> None:
+    """Per-shard search whose sorted key rows go straight into the inbox of the rank owning each
+    query (``inbox_table``: int64 device tensor of one ``[n_ranks, nq_per_rank, k]`` inbox pointer per
+    rank, local or peer memory) - the producer half of the query-owner exchange."""
+    _cuda(corpus, "corpus"); _cuda(queries, "queries"); _cuda(inbox_table, "inbox_table")
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    d = corpus.shape[1]
+    nq = queries.shape[0]
+    dev = corpus.device
+    code = dtype_code(corpus.dtype)
+    ws = _workspace(dev, int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, code, nq, k)), "dense")
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_dense_topk_keys_push(corpus.data_ptr(), n, d, code, queries.data_ptr(), nq, k,
+                                                  int(id_base), inbox_table.data_ptr(), inbox_table.numel(),
+                                                  int(rank), int(nq_per_rank), ws.data_ptr(), ws.numel(),
+                                                  path, None, _stream_ptr(dev)), "dense_topk_keys_push")
+
+
 def merge_topk_keys(keys: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """keys: [G, nq, k_in] packed keys (as all-gathered) -> merged (scores, ids)."""
     _cuda(keys, "keys")

@@ -60,6 +60,43 @@ class _PeerExchange:
         return ops.merge_topk_keys_p2p(self.tables[slot], self.nq, self.k, k_out)
 
 
+class _OwnerExchange:
+    """Query-owner exchange for one (nq, k) shape: rank g owns queries ``[g*nq_per, (g+1)*nq_per)``;
+    every rank's merge kernel PUSHES the sorted key row of each query into its owner's inbox
+    (symmetric memory, stores over NVLink), one device-side barrier orders the stores, and every
+    rank merges only the ``world`` lists of its own queries out of local memory.  Compared with
+    every rank merging all ``nq`` queries from peer memory this divides the cross-shard merge work
+    by ``world`` and turns remote loads (a round trip each) into fire-and-forget stores."""
+
+    def __init__(self, nq: int, k: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        self.nq, self.k = nq, k
+        self.nq_per = (nq + self.world - 1) // self.world
+        self.q_lo = min(nq, self.rank * self.nq_per)
+        self.q_hi = min(nq, self.q_lo + self.nq_per)
+        self.inbox = symm_mem.empty((2, self.world, self.nq_per, k), dtype=torch.int64, device=device)
+        self.inbox.zero_()
+        self.hdl = symm_mem.rendezvous(self.inbox, grp)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        slot_bytes = self.world * self.nq_per * k * 8
+        self.tables = [torch.tensor([p + s * slot_bytes for p in ptrs], dtype=torch.int64, device=device)
+                       for s in range(2)]
+        self.step = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=grp)                      # every inbox is zeroed before anybody pushes
+
+    def push_and_merge(self, push, k_out: int):
+        slot = self.step & 1
+        self.step += 1
+        push(self.tables[slot])                      # this rank's key rows -> the owners' inboxes
+        self.hdl.barrier(channel=slot)               # all rows of this search have landed
+        scores, rows = ops.merge_topk_keys(self.inbox[slot], k_out)
+        n_own = self.q_hi - self.q_lo
+        return scores[:n_own], rows[:n_own]
+
+
 class ShardedFlatIndex:
     def __init__(self, rows: torch.Tensor, id_base: int, n_rows: Optional[int] = None, group=None,
                  exchange: str = "auto"):
@@ -74,6 +111,7 @@ class ShardedFlatIndex:
         self.exchange = os.environ.get("RAGARC_EXCHANGE", exchange)
         self._gather_buf = None
         self._peer = {}
+        self._owner = {}
         self._peer_failed = False
         self.exchange_used = "none" if self.world == 1 else "nccl"
 
@@ -99,24 +137,66 @@ class ShardedFlatIndex:
             self._peer[key] = px
         return px
 
-    def capture(self, queries: torch.Tensor, k: int):
+    def owned_range(self, nq: int) -> Tuple[int, int]:
+        """Queries ``[lo, hi)`` of an ``nq``-query batch whose results ``search_owned`` leaves on this rank."""
+        per = (nq + self.world - 1) // self.world
+        lo = min(nq, self.rank * per)
+        return lo, min(nq, lo + per)
+
+    def search_owned(self, queries: torch.Tensor, k: int):
+        """Like ``search``, but the merged result of every query ends up only on the rank that owns
+        it (``owned_range``): returns ``(scores float32 [n_own,k], global rows int64 [n_own,k])``.
+        Every rank still receives and scores the full batch against its shard; what is partitioned is
+        the cross-shard merge and the result (a host gathers the slices, or each rank answers for
+        its queries).  Needs peer memory; falls back to ``search`` + slicing otherwise."""
+        nq = queries.shape[0]
+        lo, hi = self.owned_range(nq)
+        if self.world == 1 or self.exchange == "nccl" or self._peer_failed:
+            s, r = self.search(queries, k)
+            return s[lo:hi], r[lo:hi]
+        ox = self._owner.get((nq, k))
+        if ox is None:
+            err = None
+            try:
+                ox = _OwnerExchange(nq, k, self.rows.device, self.group)
+            except Exception as exc:  # noqa: BLE001 - symmetric memory not available on this system
+                if self.exchange == "peer":
+                    raise
+                err, ox = exc, None
+            ok = torch.tensor([1 if ox is not None else 0], device=self.rows.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._peer_failed = True
+                if self.rank == 0:
+                    print(f"[rag_arc_b200.sharded] owner exchange unavailable "
+                          f"({type(err).__name__ if err else 'peer rank'}: {err}); using NCCL all-gather")
+                s, r = self.search(queries, k)
+                return s[lo:hi], r[lo:hi]
+            self._owner[(nq, k)] = ox
+        self.exchange_used = "owner-push"
+        return ox.push_and_merge(
+            lambda table: ops.dense_topk_keys_push(self.rows, queries, k, self.id_base, table, self.rank,
+                                                   ox.nq_per, n_rows=self.n_local), k)
+
+    def capture(self, queries: torch.Tensor, k: int, owned: bool = False):
         """CUDA-graph the whole search (scoring, key exchange, merge) for a fixed query buffer:
         returns ``(replay, scores, rows)``; refill ``queries`` in place and call ``replay()``.
         At small shards the step is a handful of ~0.1 ms kernels and host launch overhead shows."""
-        self.search(queries, k)                    # warm-up: allocations, peer rendezvous
-        self.search(queries, k)                    # both buffer slots have been used once
+        search = self.search_owned if owned else self.search
+        search(queries, k)                         # warm-up: allocations, peer rendezvous
+        search(queries, k)                         # both buffer slots have been used once
         torch.cuda.synchronize()
         side = torch.cuda.Stream(queries.device)
         side.wait_stream(torch.cuda.current_stream(queries.device))
         graphs, outs = [], []
         with torch.cuda.stream(side):
-            self.search(queries, k)
-            self.search(queries, k)                # workspaces of the capture stream exist now
+            search(queries, k)
+            search(queries, k)                     # workspaces of the capture stream exist now
             side.synchronize()
             for _ in range(2):                     # one graph per exchange-buffer slot
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    outs.append(self.search(queries, k))
+                    outs.append(search(queries, k))
                 graphs.append(g)
         torch.cuda.current_stream(queries.device).wait_stream(side)
         state = {"i": 0}
@@ -230,14 +310,21 @@ class ShardedSearchPipeline:
     pipeline is in use the index must not be searched through any other route (a full
     ``dist.barrier()`` + device synchronise separates it from earlier work)."""
 
-    def __init__(self, index: ShardedFlatIndex, prepare, nq: int, d: int, k: int):
+    def __init__(self, index: ShardedFlatIndex, prepare, nq: int, d: int, k: int, owned: bool = False):
+        """owned=True: every rank returns only the results of the queries it owns
+        (``index.owned_range(nq)``; query-owner exchange) instead of all ``nq``."""
         self.index, self.nq, self.k = index, nq, k
+        self.owned = owned
+        search = index.search_owned if owned else index.search
+        lo, hi = index.owned_range(nq) if owned else (0, nq)
+        self.q_lo, self.q_hi = lo, hi
+        n_out = hi - lo
         dev = index.rows.device
         self.dev = dev
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         q32s = [torch.zeros((nq, d), dtype=torch.float32, device=dev) for _ in range(2)]
         for q32 in q32s:                                   # allocations, peer rendezvous
-            index.search(prepare(q32), k)
+            search(prepare(q32), k)
         torch.cuda.synchronize(dev)
         if index.world > 1:
             dist.barrier(group=index.group)
@@ -246,16 +333,16 @@ class ShardedSearchPipeline:
         self.slots = []
         with torch.cuda.stream(side):
             for q32 in q32s:                               # workspaces of the capture stream exist now
-                index.search(prepare(q32), k)
+                search(prepare(q32), k)
             side.synchronize()
             for q32 in q32s:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    scores, rows = index.search(prepare(q32), k)
+                    scores, rows = search(prepare(q32), k)
                 self.slots.append({
                     "q32": q32, "graph": g, "scores": scores, "rows": rows,
-                    "h_scores": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
-                    "h_rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                    "h_scores": torch.empty((n_out, k), dtype=torch.float32).pin_memory(),
+                    "h_rows": torch.empty((n_out, k), dtype=torch.int64).pin_memory(),
                     "copied_in": torch.cuda.Event(), "computed": torch.cuda.Event(),
                     "copied_out": torch.cuda.Event(), "busy": False,
                 })

@@ -21,3 +21,15 @@ def dev():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are skipped (not failed) on a host without a CUDA device, whether or not they
+    request the ``dev`` fixture."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -81,13 +81,16 @@ def test_dense_plan_introspection_without_a_gpu():
     from rag_arc_b200 import _native as N
     p = N.dense_plan(1_000_000, 768, N.BF16, 1024, 100)
     assert p["path"] == N.DENSE_TCGEN05 and p["rows_per_item"] == 256 and p["query_blocks"] == 4
-    assert p["slices"] * 100 <= 16384 and p["seed_rows"] % 256 == 0 and 0 < p["seed_rows"] <= 16384
+    # thresholds come from published order statistics (>= k rows behind the minimum), not a seed pass
+    assert p["slices"] * 100 <= 16384 and p["seed_rows"] == 0
+    assert 0 < p["publishing_lists"] <= 32 and 0 < p["published_rank"] <= 8
+    assert p["publishing_lists"] * p["published_rank"] >= 100
     assert 0 <= p["tail_slices"] < p["slices"] and 0 < p["cluster_tiles"] <= 3907
     p1 = N.dense_plan(1_000_000, 768, N.BF16, 1, 100)
     assert p1["rows_per_item"] == 128 and p1["pairs_per_cluster"] == 1 and p1["query_blocks"] == 1
     pf = N.dense_plan(10_000, 384, N.F32, 100, 10)
     assert pf["path"] == N.DENSE_SIMT and pf["rows_per_item"] == 64
-    out = (ctypes.c_int * 10)()
+    out = (ctypes.c_int * 16)()
     assert N.lib.ragarc_dense_topk_plan(1000, 64, N.BF16, 4, 5000, 0, out) == 4        # RAGARC_ERR_UNSUPPORTED
     assert b"2016" in N.lib.ragarc_last_error()
     assert N.lib.ragarc_dense_topk_plan(1000, 64, N.F32, 4, 5, N.DENSE_TCGEN05, out) == 4
