@@ -19,6 +19,7 @@ import asyncio
 import functools
 import logging
 import os
+import threading
 import uuid
 import warnings
 from concurrent.futures import ThreadPoolExecutor
@@ -39,6 +40,9 @@ logger = logging.getLogger(__name__)
 def default_preprocessing_func(text: str) -> List[str]:
     """Whitespace tokenisation (English only), the reference default (bm25.py:16-25)."""
     return text.split()
+
+
+_load_device = threading.local()      # set by load_from_disk while it unpickles a natively saved vectorizer
 
 
 class B200BM25Okapi:
@@ -77,9 +81,12 @@ class B200BM25Okapi:
 
     def __setstate__(self, st):
         self.k1, self.b, self.epsilon, self.tokenizer = st["k1"], st["b"], st["epsilon"], st["tokenizer"]
+        # the device asked for by the loader (BM25Retriever.load_from_disk(device=...)) wins over the
+        # one the state happened to be saved from
+        device = getattr(_load_device, "value", None) or st["device"]
         self.index = Bm25Index(vocab=st["vocab"], indptr=st["indptr"], post_doc=st["post_doc"],
                                post_tf=st["post_tf"], doc_len=st["doc_len"], k1=self.k1, b=self.b,
-                               epsilon=self.epsilon, device=st["device"])
+                               epsilon=self.epsilon, device=device)
 
 
 class BM25Retriever(BaseRetriever):
@@ -97,6 +104,7 @@ class BM25Retriever(BaseRetriever):
             raise ValueError("preprocess_func must be callable")
         self.bm25_params: Dict[str, Any] = kwargs.pop("bm25_params", None) or {}
         self.device = kwargs.pop("device", "cuda")
+        self._version = 0            # bumped by every rebuild / add / delete (row -> Document caches key on it)
         super().__init__(**kwargs)
         if warn_flag and self.preprocess_func == default_preprocessing_func and not explicit_pre:
             warnings.warn("using the default whitespace tokenizer; provide preprocess_func for Chinese or other "
@@ -141,6 +149,7 @@ class BM25Retriever(BaseRetriever):
                               bm25_params=bm25_params, preprocess_func=preprocess_func, **kwargs)
 
     def _rebuild(self) -> None:
+        self._version += 1
         tokens = [self.preprocess_func(d.content) for d in self.docs]
         self.vectorizer = B200BM25Okapi(tokens, device=self.device, **self.bm25_params)
 
@@ -187,6 +196,11 @@ class BM25Retriever(BaseRetriever):
     def row_documents(self) -> List[Document]:
         return self.docs
 
+    def corpus_stamp(self):
+        """Changes whenever the row -> Document mapping may have changed (a delete followed by an add
+        of equal size keeps ``len(docs)`` but moves rows): mutation counter + identity of the list."""
+        return (self._version, id(self.docs), len(self.docs))
+
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
         if not self.docs:
             return [[] for _ in queries]
@@ -212,6 +226,7 @@ class BM25Retriever(BaseRetriever):
             return await loop.run_in_executor(pool, functools.partial(self.add_documents, documents, **kwargs))
 
     def delete_documents(self, ids: Optional[List[str]] = None, **kwargs: Any) -> bool:
+        self._version += 1
         if ids is None:
             self.docs.clear()
             self.vectorizer = None
@@ -269,16 +284,22 @@ class BM25Retriever(BaseRetriever):
             raise IOError(f"save failed: {exc}")
 
     @classmethod
-    def load_from_disk(cls, path: str, device: str = "cuda") -> "BM25Retriever":
+    def load_from_disk(cls, path: str, device: Optional[str] = None) -> "BM25Retriever":
         """Loads a file written by ``save_to_disk`` - this class's or the REFERENCE's
         (core/retrieval/bm25.py:550-576).  A reference file carries a ``rank_bm25.BM25Okapi``; its
         parameters (k1, b, epsilon) are taken over and the CSR index is rebuilt from the documents
-        with the stored tokeniser, which reproduces the reference's idf table bit for bit."""
+        with the stored tokeniser, which reproduces the reference's idf table bit for bit.
+        ``device``: where the index goes; ``None`` = the device a natively saved state came from
+        ("cuda" for a reference file)."""
         if not os.path.exists(path):
             raise IOError(f"file does not exist: {path}")
         try:
             from ...formats import ForeignBM25, load_reference_bm25_state
-            st = load_reference_bm25_state(path)
+            _load_device.value = device
+            try:
+                st = load_reference_bm25_state(path)
+            finally:
+                _load_device.value = None
             vec = st["vectorizer"]
             pre = st.get("preprocess_func") or default_preprocessing_func
             params = dict(st.get("bm25_params") or {})
@@ -286,8 +307,9 @@ class BM25Retriever(BaseRetriever):
                 for name in ("k1", "b", "epsilon"):
                     if hasattr(vec, name):
                         params.setdefault(name, getattr(vec, name))
-                vec = B200BM25Okapi([pre(d.content) for d in st["docs"]], device=device, **params)
+                vec = B200BM25Okapi([pre(d.content) for d in st["docs"]], device=device or "cuda", **params)
             return cls(vectorizer=vec, docs=st["docs"], k=st["k"], preprocess_func=pre,
-                       bm25_params=st.get("bm25_params") or {}, warn_default_preprocess=False, device=device)
+                       bm25_params=st.get("bm25_params") or {}, warn_default_preprocess=False,
+                       device=str(vec.index.device))
         except Exception as exc:
             raise IOError(f"load failed: {exc}")

@@ -99,6 +99,11 @@ class VectorStoreRetriever(BaseRetriever):
             self._row_docs = cached
         return cached[1]
 
+    def corpus_stamp(self):
+        """Changes whenever the store's row -> Document mapping may have changed."""
+        vs = self.vectorstore
+        return (getattr(vs, "_version", None), id(getattr(vs, "index_to_docstore_id", None)), vs.ntotal)
+
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
         params = self._resolve(kwargs)
         if self.search_type != "similarity" or not hasattr(self.vectorstore, "search_batch"):

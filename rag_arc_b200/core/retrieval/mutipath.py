@@ -48,8 +48,11 @@ class MultiPathRetriever(BaseRetriever):
     # ---- batched hybrid (B200 addition) ------------------------------------------------------------
     def _canonical_tables(self, device):
         """content -> integer key (first appearance over the retrievers, in order) and, per
-        retriever, a device table row -> key.  Rebuilt when a retriever's corpus size changes."""
-        sig = tuple(len(r.row_documents()) for r in self.retrievers)
+        retriever, a device table row -> key.  Rebuilt when any retriever reports a different
+        ``corpus_stamp()`` (mutation counter, not just the corpus size: a delete followed by an add of
+        the same number of documents moves rows without changing the size)."""
+        sig = tuple((id(r), r.corpus_stamp()) if hasattr(r, "corpus_stamp")
+                    else (id(r), id(r.row_documents()), len(r.row_documents())) for r in self.retrievers)
         if self._canon_cache is not None and self._canon_cache[0] == sig:
             return self._canon_cache[1], self._canon_cache[2]
         keys: Dict[str, int] = {}

@@ -130,18 +130,22 @@ class FlatIndexB200:
     def capture_search(self, queries: torch.Tensor, k: int):
         """CUDA-graph ``search_device`` for a fixed, already prepared query buffer: returns
         ``(replay, scores, rows)``; refill ``queries`` in place, call ``replay()``."""
-        self.search_device(queries, k)
         torch.cuda.synchronize()
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            self.search_device(queries, k)         # workspace of the capture stream exists now
+        scope = ops.WorkspaceScope()               # the graph's own scratch buffers (kept alive with it)
+        with scope, torch.cuda.stream(side):
+            self.search_device(queries, k)         # the scope's workspaces exist now
             side.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 scores, rows = self.search_device(queries, k)
         torch.cuda.current_stream(self.device).wait_stream(side)
-        return g.replay, scores, rows
+
+        def replay(_g=g, _scope=scope):
+            _g.replay()
+
+        return replay, scores, rows
 
     def search(self, q, k: int):
         """faiss-style: numpy in, ``(D float32 [nq,k], I int64 [nq,k])`` numpy out."""
@@ -177,6 +181,8 @@ class SearchPipeline:
         self.n_submitted = 0
         self.use_graph = graph
         self._captured_for = None
+        self._scope = None
+        self._eager_scope = ops.WorkspaceScope()
         if graph:
             self._capture()
 
@@ -193,8 +199,11 @@ class SearchPipeline:
             torch.cuda.synchronize(dev)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for slot in self.slots:                    # workspaces of the capture stream exist now
+            # scratch buffers owned by this pipeline: the slots replay one after the other on s_cmp, so
+            # they may share them, but nothing outside the pipeline can touch or replace them
+            self._scope = ops.WorkspaceScope()
+            with self._scope, torch.cuda.stream(side):
+                for slot in self.slots:                    # the scope's workspaces exist now
                     self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
                 side.synchronize()
                 for slot in self.slots:
@@ -236,7 +245,8 @@ class SearchPipeline:
             if slot["graph"] is not None:
                 slot["graph"].replay()
             else:
-                slot["scores"], slot["rows"] = self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
+                with self._eager_scope:
+                    slot["scores"], slot["rows"] = self.index.search_device(self.index.prepare_queries(slot["q32"]), self.k)
             slot["computed"].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["computed"])
@@ -309,6 +319,8 @@ class B200VectorStore(VectorStore):
                        ids: Optional[List[str]] = None) -> List[str]:
         """Append pre-computed embeddings (fp32 ``[n,d]`` numpy or tensor, host or device)."""
         texts = list(texts)
+        if getattr(vectors, "ndim", 2) != 2 or int(vectors.shape[0]) != len(texts):
+            raise ValueError(f"number of vectors ({tuple(vectors.shape)}) must match number of texts ({len(texts)})")
         if self.index is None:
             self.index = self._create_index(int(vectors.shape[1]))
         if ids is None:
@@ -503,19 +515,36 @@ class B200VectorStore(VectorStore):
             kwargs.setdefault("dtype", "float32")
         store = cls(embedding=embeddings, index_type=side["index_type"], metric=side["metric"],
                     normalize_L2=side["normalize_L2"], **kwargs)
+        n_side = len(side["index_to_docstore_id"])
         if os.path.exists(path):
-            host = torch.from_numpy(np.load(path))
+            arr = np.load(path)
+            want = {torch.bfloat16: (np.int16, np.uint16), torch.float16: (np.float16,), torch.float32: (np.float32,)}[store.dtype]
+            if arr.ndim != 2 or arr.dtype.type not in want:
+                raise ValueError(f"{path}: holds {arr.dtype} {arr.shape}, the sidecar says dtype {side.get('dtype')}")
+            host = torch.from_numpy(arr)
             if store.dtype == torch.bfloat16:
                 host = host.view(torch.bfloat16)
             store.index = store._create_index(int(host.shape[1]))
             store.index.add_prepared(host.to(store.device))
         elif os.path.exists(faiss_path):
             # a folder written by the reference's FaissVectorStore.save_local (:432-450): fp32 rows of
-            # a flat index, already normalised by the reference when its metric was cosine (normalising
-            # them again on add is idempotent up to one ulp); `dtype=` chooses the B200 storage type
+            # a flat index, ALREADY normalised by the reference when its metric was cosine (:178) - they
+            # are taken over as stored (normalising again would move them by an ulp for no reason);
+            # `dtype=` chooses the B200 storage type, i.e. at most a cast happens here
             rows, _ = read_faiss_flat(faiss_path)
             store.index = store._create_index(int(rows.shape[1]))
-            store.index.add(rows)
+            prepared = torch.from_numpy(np.ascontiguousarray(rows)).to(store.device)
+            store.index.add_prepared(prepared if store.dtype == torch.float32 else prepared.to(store.dtype))
+        # the sidecar must describe exactly the rows that were loaded: a truncated or mismatched folder
+        # fails here, not with a KeyError (or a wrong document) at search time
+        n_rows = 0 if store.index is None else store.index.ntotal
+        if n_rows != n_side:
+            raise ValueError(f"{folder_path}: the row file holds {n_rows} vectors but the sidecar maps {n_side} rows")
+        if n_side and sorted(side["index_to_docstore_id"]) != list(range(n_side)):
+            raise ValueError(f"{folder_path}: index_to_docstore_id is not a dense 0..{n_side - 1} row map")
+        missing = [i for i in side["index_to_docstore_id"].values() if i not in side["docstore"]]
+        if missing:
+            raise ValueError(f"{folder_path}: {len(missing)} mapped ids are missing from the docstore (first: {missing[0]!r})")
         store.docstore = side["docstore"]
         store.index_to_docstore_id = side["index_to_docstore_id"]
         return store

@@ -100,13 +100,30 @@ class _ReferenceUnpickler(pickle.Unpickler):
     _SAFE_BUILTINS = {"set": set, "frozenset": frozenset, "bytearray": bytearray, "complex": complex,
                       "range": range, "slice": slice}
 
+    # inert value types that commonly sit in Document.metadata (timestamps, ids, numpy numbers and
+    # small arrays, paths): constructing them runs no user code
+    _SAFE_VALUES = {
+        "datetime": ("datetime", "date", "time", "timedelta", "timezone"),
+        "decimal": ("Decimal",), "uuid": ("UUID",), "fractions": ("Fraction",),
+        "collections": ("OrderedDict", "defaultdict", "deque", "Counter"),
+        "pathlib": ("PurePosixPath", "PosixPath", "PureWindowsPath", "WindowsPath"),
+        "numpy": ("dtype", "ndarray", "float32", "float64", "int32", "int64", "bool_", "str_"),
+        "numpy.core.multiarray": ("scalar", "_reconstruct"), "numpy._core.multiarray": ("scalar", "_reconstruct"),
+        "numpy.core.numeric": ("_frombuffer",), "numpy._core.numeric": ("_frombuffer",),
+    }
+
     def find_class(self, module: str, name: str):
         if module == "builtins" and name in self._SAFE_BUILTINS:      # plain containers inside metadata
             return self._SAFE_BUILTINS[name]
+        if name in self._SAFE_VALUES.get(module, ()):
+            import importlib
+            return getattr(importlib.import_module(module), name)
         try:
             return self._ALLOWED[(module, name)]
         except KeyError:
-            raise pickle.UnpicklingError(f"sidecar refers to {module}.{name}; only Document objects are expected") from None
+            raise pickle.UnpicklingError(
+                f"sidecar refers to {module}.{name}; only Document objects and plain value types "
+                "(datetime, Decimal, UUID, numpy scalars/arrays, paths, collections) are admitted") from None
 
 
 def load_reference_sidecar(path: str) -> Dict[str, Any]:

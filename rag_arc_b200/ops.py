@@ -34,8 +34,47 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_tls = threading.local()
+
+
+class WorkspaceScope:
+    """Scratch buffers owned by one user instead of the per-stream cache.  A CUDA graph bakes the raw
+    pointers of the workspaces its kernels were captured with, so everything that captures (search
+    pipelines, ``capture_search``) runs its warm-up AND its capture inside a scope of its own and keeps
+    the scope alive next to the graph: no later call on the same (pooled) stream can grow, replace or
+    share those buffers.  Buffers that had to grow inside the scope are retired, not freed."""
+
+    def __init__(self):
+        self.bufs: dict = {}
+        self.retired: list = []
+        self._prev = None
+
+    def __enter__(self):
+        self._prev = getattr(_tls, "scope", None)
+        _tls.scope = self
+        return self
+
+    def __exit__(self, *exc):
+        _tls.scope = self._prev
+        return False
+
+    def get(self, device, nbytes: int, tag: str) -> torch.Tensor:
+        key = (device.index, tag)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                self.retired.append(buf)
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
+
+
 def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream, purpose); stream order makes reuse safe."""
+    """Scratch buffer: the active ``WorkspaceScope``'s if there is one (graph captures), else a
+    grow-only buffer per (device, stream, purpose) - stream order makes that reuse safe."""
+    scope = getattr(_tls, "scope", None)
+    if scope is not None:
+        return scope.get(device, nbytes, tag)
     key = (device.index, _stream_ptr(device), tag)
     with _ws_lock:
         buf = _ws_cache.get(key)

@@ -189,9 +189,10 @@ class ShardedFlatIndex:
         side = torch.cuda.Stream(queries.device)
         side.wait_stream(torch.cuda.current_stream(queries.device))
         graphs, outs = [], []
-        with torch.cuda.stream(side):
+        scope = ops.WorkspaceScope()               # scratch buffers owned by these graphs
+        with scope, torch.cuda.stream(side):
             search(queries, k)
-            search(queries, k)                     # workspaces of the capture stream exist now
+            search(queries, k)                     # the scope's workspaces exist now
             side.synchronize()
             for _ in range(2):                     # one graph per exchange-buffer slot
                 g = torch.cuda.CUDAGraph()
@@ -199,7 +200,7 @@ class ShardedFlatIndex:
                     outs.append(search(queries, k))
                 graphs.append(g)
         torch.cuda.current_stream(queries.device).wait_stream(side)
-        state = {"i": 0}
+        state = {"i": 0, "scope": scope}
         scores, rows = outs[0]
 
         def replay():
@@ -331,8 +332,9 @@ class ShardedSearchPipeline:
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         self.slots = []
-        with torch.cuda.stream(side):
-            for q32 in q32s:                               # workspaces of the capture stream exist now
+        self._scope = ops.WorkspaceScope()                 # scratch buffers owned by this pipeline's graphs
+        with self._scope, torch.cuda.stream(side):
+            for q32 in q32s:                               # the scope's workspaces exist now
                 search(prepare(q32), k)
             side.synchronize()
             for q32 in q32s:

@@ -58,6 +58,68 @@ def test_sharded_search_equals_single_gpu(exchange):
     assert ok == 1, f"mismatch (exchange used: {used})"
 
 
+def _owner_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from rag_arc_b200 import ops, sharded, synth
+    n, d, nq, k = 300_001, 128, 203, 50                                    # nq not divisible by the world size
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=3)
+    q, _ = synth.dense_queries_cuda(x, nq, seed=4)
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    idx = sharded.ShardedFlatIndex(x[lo:hi].contiguous(), lo)
+    s_ref, i_ref = ops.dense_topk(x, q, k)
+    qlo, qhi = idx.owned_range(nq)
+    ok = True
+    for it in range(4):                                                     # both inbox slots, twice
+        s, i = idx.search_owned(q, k)
+        ok = ok and bool(torch.equal(i, i_ref[qlo:qhi]) and torch.equal(s, s_ref[qlo:qhi]))
+    ok = ok and idx.exchange_used == "owner-push"
+    replay, s, i = idx.capture(q, k, owned=True)
+    for it in range(3):
+        s, i = replay()
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(i, i_ref[qlo:qhi]) and torch.equal(s, s_ref[qlo:qhi]))
+    prepare = lambda q32: ops.normalize_cast(q32, torch.bfloat16, True)
+    pipe = sharded.ShardedSearchPipeline(idx, prepare, nq, d, k, owned=True)
+    batches = [torch.randn((nq, d), generator=torch.Generator().manual_seed(100 + b)).pin_memory() for b in range(4)]
+    prev, results = None, []
+    for b in batches:
+        t = pipe.submit(b)
+        if prev is not None:
+            hs, hr = pipe.result(prev); results.append((hs.clone(), hr.clone()))
+        prev = t
+    hs, hr = pipe.result(prev); results.append((hs.clone(), hr.clone()))
+    for b, (hs, hr) in zip(batches, results):
+        sr, ir = ops.dense_topk(x, prepare(b.to(dev)), k)
+        ok = ok and bool(torch.equal(hr, ir[qlo:qhi].cpu()) and torch.equal(hs, sr[qlo:qhi].cpu()))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_query_owner_exchange_equals_single_gpu():
+    """search_owned (merge kernel pushes key rows into the owner's inbox over NVLink, every rank merges
+    its own queries): eager, CUDA-graphed and through the host pipeline, against the single-GPU result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owner_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert out.get() == 1
+
+
 def _bm25_worker(rank, world, port, out):
     import numpy as np
     import torch.distributed as dist

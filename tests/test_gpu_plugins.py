@@ -286,6 +286,34 @@ def test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fus
     assert [[d.content for d in b] for b in batch] == [[d.content for d in s] for s in single]
 
 
+def test_hybrid_batch_follows_an_update_that_keeps_the_corpus_size(dev):
+    """delete + add of the same number of documents moves rows but keeps every size: the cached
+    row -> key tables of ``invoke_batch`` must be rebuilt (they are keyed on mutation stamps), so the
+    batch result keeps equal to the single-query path on both retrievers."""
+    from rag_arc_b200.core.retrieval.bm25 import BM25Retriever
+    texts_a = [f"alpha{i} common words here" for i in range(8)]
+    texts_b = [f"beta{i} other common words" for i in range(8)]
+    ra = BM25Retriever.from_texts(texts_a, ids=[f"a{i}" for i in range(8)], device=dev)
+    rb = BM25Retriever.from_texts(texts_b, ids=[f"b{i}" for i in range(8)], device=dev)
+    mp = MultiPathRetriever([ra, rb], fusion_method=RRFusion(device=dev), top_k_per_retriever=4)
+    queries = ["alpha4 common", "beta2 words", "alpha1 alpha0"]
+
+    def same():
+        batch = mp.invoke_batch(queries, top_k=4)
+        single = [mp.invoke(q, top_k=4) for q in queries]
+        assert all(d is not None for b in batch for d in b)
+        assert [[d.content for d in b] for b in batch] == [[d.content for d in s_] for s_ in single]
+
+    same()
+    ra.delete_documents(["a2"])                       # rows of a3.. move up by one
+    ra.add_documents([Document(content="alpha2 replaced text", metadata={}, id="a2x")])
+    assert ra.get_document_count() == 8
+    same()
+    rb.delete_documents(["b0", "b5"])
+    rb.add_documents([Document(content="beta9 new", metadata={}, id="b9"), Document(content="beta10 new", metadata={}, id="b10")])
+    same()
+
+
 def test_registry_builds_hybrid_retriever_from_json(dev, tmp_path):
     from rag_arc_b200.configs import HybridRetrieverConfig
     from rag_arc_b200.framework import Register
@@ -351,3 +379,53 @@ def test_load_local_imports_a_folder_saved_by_the_reference(dev):
     assert half.dtype == torch.bfloat16 and half.ntotal == 60
     res = half.similarity_search_by_vector_with_score(z["qvecs"][0].tolist(), k=1)
     assert res[0][0].id == f"id{I[0][0]}"
+
+
+def test_load_local_keeps_reference_rows_bitwise_and_validates_the_folder(dev, tmp_path):
+    """(1) A cosine store saved by the reference holds already normalised rows: load_local takes them
+    over bit for bit (no second normalisation).  (2) A folder whose sidecar does not describe its row
+    file fails at load time with ValueError.  (3) A sidecar whose metadata holds plain value types
+    (datetime, numpy scalars) loads; one that names any other class is refused."""
+    import datetime
+    import pickle
+    import shutil
+    from rag_arc_b200 import formats
+    folder = os.path.join(GOLD, "ref_saved_store")
+    rows, _ = formats.read_faiss_flat(os.path.join(folder, "index.faiss"))
+    store = B200VectorStore.load_local(folder, TableEmbeddings({}), device=dev)
+    assert np.array_equal(store.index.rows[:store.ntotal].cpu().numpy().view(np.uint32), rows.view(np.uint32))
+    # (2) truncated row file / foreign id
+    bad = tmp_path / "bad"
+    shutil.copytree(folder, bad)
+    formats.write_faiss_flat(str(bad / "index.faiss"), rows[:-3], "ip")
+    with pytest.raises(ValueError, match="sidecar maps"):
+        B200VectorStore.load_local(str(bad), TableEmbeddings({}), device=dev)
+    side = formats.load_reference_sidecar(os.path.join(folder, "index.pkl"))
+    side["index_to_docstore_id"][0] = "not-there"
+    bad2 = tmp_path / "bad2"
+    shutil.copytree(folder, bad2)
+    with open(bad2 / "index.pkl", "wb") as fh:
+        pickle.dump(side, fh)
+    with pytest.raises(ValueError, match="missing from the docstore"):
+        B200VectorStore.load_local(str(bad2), TableEmbeddings({}), device=dev)
+    # (3) value types in metadata
+    ok = B200VectorStore(embedding=TableEmbeddings({}), metric="ip", dtype="float32", device=dev)
+    vec = np.eye(4, dtype=np.float32)
+    metas = [{"when": datetime.datetime(2024, 5, 1, 12, 0), "score": np.float32(0.5), "n": np.int64(3)} for _ in range(4)]
+    ok.add_embeddings([f"t{i}" for i in range(4)], vec, metas, ids=[f"i{i}" for i in range(4)])
+    ok.save_local(str(tmp_path / "ok"))
+    back = B200VectorStore.load_local(str(tmp_path / "ok"), TableEmbeddings({}), device=dev)
+    assert back.docstore["i2"].metadata["when"] == datetime.datetime(2024, 5, 1, 12, 0)
+    assert back.docstore["i2"].metadata["score"] == np.float32(0.5) and back.docstore["i2"].metadata["n"] == 3
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    side_evil = {"docstore": {}, "index_to_docstore_id": {}, "index_type": "flat", "metric": "ip", "normalize_L2": False,
+                 "x": Evil()}
+    with open(tmp_path / "evil.pkl", "wb") as fh:
+        pickle.dump(side_evil, fh)
+    with pytest.raises(pickle.UnpicklingError):
+        formats.load_reference_sidecar(str(tmp_path / "evil.pkl"))
+    with pytest.raises(ValueError, match="must match number of texts"):
+        ok.add_embeddings(["a", "b"], vec[:3], None)

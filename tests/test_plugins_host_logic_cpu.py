@@ -47,6 +47,10 @@ def test_hybrid_retriever_with_ties_and_duplicates():
     T.test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fusion_oracle(CPU)
 
 
+def test_hybrid_batch_follows_an_update_that_keeps_the_corpus_size():
+    T.test_hybrid_batch_follows_an_update_that_keeps_the_corpus_size(CPU)
+
+
 def test_registry_builds_hybrid_retriever(tmp_path):
     """Same JSON as the GPU test, with every ``device`` field pointing at the CPU stand-ins."""
     import json
@@ -77,3 +81,7 @@ def test_pooled_embeddings_plugin():
 
 def test_load_local_imports_reference_folder():
     T.test_load_local_imports_a_folder_saved_by_the_reference(CPU)
+
+
+def test_load_local_bitwise_rows_and_folder_validation(tmp_path):
+    T.test_load_local_keeps_reference_rows_bitwise_and_validates_the_folder(CPU, tmp_path)
