@@ -144,7 +144,8 @@ class IndexFlatIP:
 
     def search(self, q: np.ndarray, k: int):
         q = np.ascontiguousarray(q, dtype=np.float32)
-        return flat_ip_search(self._x, q, k)
+        # large blocks: FAISS scans the whole matrix per query; small blocks would only add Python overhead
+        return flat_ip_search(self._x, q, k, block=1 << 20)
 
 
 class IndexFlatL2(IndexFlatIP):

@@ -10,8 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
+    # torchrun hands OMP_NUM_THREADS=1 to its workers: the arm must still use every host thread it may
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1"], capture_output=True, text=True, timeout=900)
+                          "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -20,7 +22,7 @@ def test_reference_arm_prints_one_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
-    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["n_gpus"] == 2 and d["steps"] == 1
     assert d["config"]["workload"] == "c3" and d["config"]["rows"] == 1_000_000 and d["config"]["dim"] == 768
     assert d["config"]["batch"] == 1024 and d["config"]["k"] == 100 and "model" not in d["config"]
     assert "1M x 768" in d["metric"] and d["value"] > 0 and d["ms_per_step"] > 0
@@ -28,6 +30,12 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert cb["cores"] == len(os.sched_getaffinity(0)) and d["host"]["torch_threads"] == cb["cores"]
+    # ranks other than 0 exit 0 without work and without output
+    env1 = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                         "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env1)
+    assert r1.returncode == 0 and not r1.stdout.strip()
 
 
 def test_gpu_arm_fails_loudly_without_a_device():
