@@ -317,7 +317,9 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a rank that falls out of step must end the run within minutes, not after NCCL's default 10
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=150))
         self.peaks = load_peaks()
         self.torch, self.dist = torch, dist
 
@@ -531,8 +533,9 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
     nrec = max(nrec, 1)
     # ---- timed region: device-resident inputs ------------------------------------------------------------
     launches0 = N.launch_count()
+    ctx.barrier()                               # every rank (a rank-conditional barrier here would deadlock the run)
     if sampler is not None:
-        ctx.barrier(); sampler.mark_begin()
+        sampler.mark_begin()
     ms_total = ctx.timed(step_device, steps)
     if sampler is not None:
         sampler.mark_end()
