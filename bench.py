@@ -394,9 +394,12 @@ def make_queries(ctx, w, batch):
     import torch
     tdtype = torch.bfloat16 if w["dtype"] == "bfloat16" else torch.float16
     if w.get("host_generated"):
+        from rag_arc_b200 import ops
         q_host = torch.from_numpy(host_queries(batch, w["dim"])).pin_memory()     # un-normalised, as handed to the plugin
         q32 = torch.nn.functional.normalize(q_host.to(ctx.dev), dim=1)
-        return q32, q32.to(tdtype).contiguous(), q_host
+        # the device-resident step searches exactly what the plugin prepares from the host batch
+        # (ragarc_normalize_cast), so that both legs must agree bit for bit
+        return q32, ops.normalize_cast(q_host.to(ctx.dev), tdtype, True), q_host
     gq = torch.Generator(device=ctx.dev); gq.manual_seed(4321)
     q32 = torch.nn.functional.normalize(torch.randn((batch, w["dim"]), generator=gq, device=ctx.dev), dim=1)
     return q32, q32.to(tdtype).contiguous(), q32.cpu().pin_memory()
