@@ -178,13 +178,26 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
  * sorted key row of query q is written straight into the inbox of the rank that owns the query,
  *   inboxes[q / nq_per_rank] + ((size_t)rank * nq_per_rank + q % nq_per_rank) * k,
  * where inboxes is a DEVICE array of n_ranks pointers, each to a [n_ranks, nq_per_rank, k] key block
- * that may live in a peer GPU's memory (stores travel over NVLink inside the merge kernel; the
- * caller orders them against the owner's ragarc_merge_topk_keys with a device-side barrier).  Every
- * rank then merges only its own nq_per_rank queries instead of all nq. */
+ * that may live in a peer GPU's memory (stores travel over NVLink inside the merge kernel).  Every
+ * rank then merges only its own nq_per_rank queries instead of all nq.
+ * signal == 0: the caller orders the stores against the owner's merge itself (a device-side barrier,
+ * then ragarc_merge_topk_keys on the inbox).
+ * signal != 0: every inbox is followed by nq_per_rank uint32 arrival counters (zero before first use,
+ *   at inbox + n_ranks*nq_per_rank*k keys); after a query's row has landed, the pushing CTA adds 1 to
+ *   the owner's counter of that query (release, system scope) and the owner calls
+ *   ragarc_merge_topk_inbox, whose CTA for query q waits for n_ranks arrivals, resets the counter and
+ *   merges - no barrier and no second round trip between the two kernels.  Use two inboxes alternately:
+ *   a rank can be at most one search ahead of the slowest one. */
 int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                                 int nq, int k, uint64_t id_base, uint64_t* const* inboxes, int n_ranks,
-                                int rank, int nq_per_rank, void* workspace, size_t workspace_bytes,
-                                int path, int* path_used_host, void* stream);
+                                int rank, int nq_per_rank, int signal, void* workspace,
+                                size_t workspace_bytes, int path, int* path_used_host, void* stream);
+/* Owner side of the signalled exchange: inbox = this rank's [n_ranks, nq_per_rank, k_in] key block +
+ * counters.  *status (device uint32, may be NULL) gets bit 0 set if a wait gave up after timeout_ms
+ * (<= 0: 2000 ms) - the results of that search are then incomplete. */
+int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int k_in, int k_out,
+                            float* out_scores, int64_t* out_ids, double timeout_ms, uint32_t* status,
+                            void* stream);
 
 /* k*G-way merge after the NCCL all-gather of ragarc_dense_topk_keys outputs.
  * keys: [nlists, nq, k_in] (as all-gathered, rank-major).  Output as ragarc_dense_topk. */

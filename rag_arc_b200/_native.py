@@ -27,7 +27,7 @@ EXPORTS = [
     "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
     "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk_plan", "ragarc_dense_topk", "ragarc_dense_topk_keys",
-    "ragarc_dense_topk_keys_push",
+    "ragarc_dense_topk_keys_push", "ragarc_merge_topk_inbox",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
@@ -85,7 +85,8 @@ def _load():
         "ragarc_dense_topk_keys": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P,
                                            c_size_t, c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys_push": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, c_int,
-                                                c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
+                                                c_int, c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_merge_topk_inbox": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_double, P, P]),
         "ragarc_normalize_split3": (c_int, [P, P, c_int64, c_int, c_int, P]),
         "ragarc_dense_topk_x3_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
         "ragarc_dense_topk_x3": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, c_size_t, P]),

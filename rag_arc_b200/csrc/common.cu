@@ -215,6 +215,8 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
   pl->off_keys = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * k * 8, 256);
   pl->off_qpad = off;   off = align_up(off + (tc ? (size_t)pl->MB * pl->rows_per_item * d * 2 : 0), 256);
   pl->off_seed = off;   off = align_up(off + (size_t)(nq > 0 ? nq : 1) * (pl->seed_rows / 16) * 4, 256);
+  // merge kernel: global gather rows for the (rare) queries whose raw candidates exceed its shared-memory array
+  pl->off_mscratch = off; off = align_up(off + (size_t)(nq > 0 ? nq : 1) * pl->S * pl->sets * pl->keep * 8, 256);
   pl->total = off;
   return RAGARC_OK;
 }
@@ -269,7 +271,8 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
     RA_CUDA(cudaEventRecord(pr.es, stream));
   }
   if (prof) RA_CUDA(cudaEventRecord(pr.e1, stream));
-  rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, out_keys, out_scores, out_ids, push, stream);
+  rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, (uint64_t*)(ws + pl.off_mscratch), out_keys,
+                          out_scores, out_ids, push, stream);
   if (rc) return rc;
   if (prof) {
     RA_CUDA(cudaEventRecord(pr.e2, stream));
@@ -378,7 +381,7 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
 
 int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,
                                 int nq, int k, uint64_t id_base, uint64_t* const* inboxes, int n_ranks,
-                                int rank, int nq_per_rank, void* workspace, size_t workspace_bytes,
+                                int rank, int nq_per_rank, int signal, void* workspace, size_t workspace_bytes,
                                 int path, int* path_used_host, void* stream) {
   RA_REQUIRE(inboxes, "dense_topk_keys_push: null inbox table");
   RA_REQUIRE(n_ranks > 0 && rank >= 0 && rank < n_ranks && nq_per_rank > 0 &&
@@ -386,7 +389,7 @@ int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype,
              "dense_topk_keys_push: bad partition n_ranks=%d rank=%d nq_per_rank=%d nq=%d", n_ranks, rank,
              nq_per_rank, nq);
   RA_REQUIRE(id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_keys_push: global ids must fit 32 bits");
-  MergePush mp{inboxes, rank, nq_per_rank};
+  MergePush mp{inboxes, rank, nq_per_rank, signal ? n_ranks : 0};
   return dense_common(corpus, n, d, dtype, queries, nq, k, id_base, nullptr, nullptr, nullptr, workspace,
                       workspace_bytes, path, path_used_host, (cudaStream_t)stream, 0, &mp);
 }

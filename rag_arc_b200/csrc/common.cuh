@@ -362,7 +362,7 @@ struct DensePlan {
   int x3_d;            // >0: rows are three bf16 planes [x1|x2|x3] of a d=x3_d fp32 vector (width 3*x3_d)
   int sets;            // tcgen05: epilogue warp sets per CTA (1 or 2) = candidate lists per (item, query row)
   int pub_n, pub_m;    // tcgen05: pub_n > 0 = the first pub_n slices publish their pub_m-th best score (replaces seeding)
-  size_t off_lists, off_counts, off_gthr, off_pub, off_keys, off_qpad, off_seed, total;
+  size_t off_lists, off_counts, off_gthr, off_pub, off_keys, off_qpad, off_seed, off_mscratch, total;
 };
 
 int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* plan, int* path_out);
@@ -384,13 +384,17 @@ struct MergePush {
   uint64_t* const* inboxes;   // device array: one inbox base pointer per rank
   int rank;                   // this rank (row of the inbox it writes)
   int nq_per;                 // queries owned by each rank (the last one may own fewer)
+  int n_ranks;                // > 0: every inbox is followed by nq_per arrival counters (uint32) at
+                              // inbox + n_ranks*nq_per*k keys; after a query's row has landed the pusher
+                              // bumps the owner's counter of that query (release, system scope), which is
+                              // what the owner's merge kernel waits on instead of a barrier between kernels
 };
 
 // merge of per-slice candidate lists -> sorted keys [nq,k] (+ optional decoded outputs); gthr (may
 // be NULL) = per-query score bound below which candidates are dropped while gathering
 int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
-                       uint64_t id_base, const uint32_t* gthr, uint64_t* out_keys, float* out_scores,
-                       int64_t* out_ids, const MergePush* push, cudaStream_t stream);
+                       uint64_t id_base, const uint32_t* gthr, uint64_t* scratch, uint64_t* out_keys,
+                       float* out_scores, int64_t* out_ids, const MergePush* push, cudaStream_t stream);
 
 int sm_count();
 int dense_tc_max_sets();              // epilogue warp sets the tcgen05 kernel was built for

@@ -9,7 +9,10 @@
 
 namespace ragarc {
 
-constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_THREADS = 512;        // seed_select_kernel
+constexpr int MERGE_LISTS_THREADS = 256;  // merge_lists_kernel: 8 CTAs per SM, all queries of a 1024-batch resident at once
+constexpr int MERGE_SMEM_KEYS = 4096;     // candidate keys a merge_lists CTA holds in shared memory; queries with more
+                                          // raw candidates (loose thresholds) gather into a global scratch row instead
 
 // k-th largest of keys[0..T) (T > k): leaves the winners (exactly k) in win[0..k), unordered.
 // hist: 256 words, sel: 3 words, nwin: 1 word of shared memory.
@@ -156,14 +159,14 @@ __device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, i
 // full radix select if more than MERGE_WIN keys survive (heavily tied scores).
 constexpr int MERGE_WIN = 512;       // survivors that are sorted directly
 
-__global__ void __launch_bounds__(MERGE_THREADS)
+__global__ void __launch_bounds__(MERGE_LISTS_THREADS)
 merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S, int sets,
-                   int rows, int cap, int k, int PK, int tmax, uint64_t id_base,
-                   const uint32_t* __restrict__ gthr, uint64_t* out_keys,
+                   int rows, int cap, int k, int PK, int tmax, int smem_keys, uint64_t* __restrict__ scratch,
+                   uint64_t id_base, const uint32_t* __restrict__ gthr, uint64_t* out_keys,
                    float* out_scores, int64_t* out_ids, MergePush push) {
   extern __shared__ uint64_t msm[];
-  uint64_t* keys = msm;                       // [tmax]
-  uint64_t* win = msm + tmax;                 // [max(PK, MERGE_WIN)] survivors / winners
+  uint64_t* keys = msm;                       // [smem_keys] (or this query's row of `scratch`, see below)
+  uint64_t* win = msm + smem_keys;            // [max(PK, MERGE_WIN)] survivors / winners
   int* offs = (int*)(win + (PK > MERGE_WIN ? PK : MERGE_WIN));   // [S+1]
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sel[3];
@@ -194,6 +197,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   __syncthreads();
   int total_raw = offs[S];
   if (total_raw > tmax) total_raw = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
+  if (total_raw > smem_keys) keys = scratch + (size_t)q * tmax;   // rare: loose thresholds; same code, global (L2) array
   // (A) flattened gather: element e of the concatenated lists belongs to the list found by binary
   // search in the prefix sums, so every load is independent of every other (a warp-per-list loop
   // serialises S/16 dependent L2 round trips).  Candidates below the query's shared threshold - a
@@ -287,6 +291,16 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   } else {
     select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
   }
+  if (push.inboxes && push.n_ranks > 0) {
+    // the row is in the owner's inbox: make it visible system-wide, then count this rank in
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int owner = q / push.nq_per;
+      uint32_t* counters = reinterpret_cast<uint32_t*>(push.inboxes[owner] + (size_t)push.n_ranks * push.nq_per * k);
+      atomicAdd_system(counters + (q - owner * push.nq_per), 1u);
+    }
+  }
 }
 
 // G per-shard result lists per query, each sorted descending (the output format of
@@ -295,16 +309,35 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
 // (binary search in shared memory); keys are unique, so ranks are a permutation.
 // list g of query q lives at (ptrs ? ptrs[g] : base + g*stride_g) + q*k_in  - with `ptrs` the lists
 // may be PEER-GPU memory (NVLink loads), which is how the multi-GPU merge avoids an all-gather.
+// counters != NULL: the lists are an inbox other GPUs write into (MergePush); the CTA of query q first
+// waits until `expected` ranks have counted themselves in for q (acquire, system scope; bounded: on
+// timeout *status is set and the merge proceeds with what is there), resets the counter for the slot's
+// next use, and reads the rows past L1.
 __global__ void __launch_bounds__(256)
-merge_sorted_keys_kernel(const uint64_t* __restrict__ base, size_t stride_g, const uint64_t* const* __restrict__ ptrs,
+merge_sorted_keys_kernel(const uint64_t* base, size_t stride_g, const uint64_t* const* __restrict__ ptrs,
                          int G, int nq, int k_in, int k_out, float* __restrict__ out_scores,
-                         int64_t* __restrict__ out_ids) {
+                         int64_t* __restrict__ out_ids, uint32_t* counters, uint32_t expected,
+                         long long timeout_cycles, uint32_t* status) {
   extern __shared__ uint64_t sk[];            // [G][k_in]
   const int q = blockIdx.x, total = G * k_in;
+  if (counters) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      uint32_t seen = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + q) : "memory");
+        if (seen >= expected) break;
+        if (clock64() - t0 > timeout_cycles) { if (status) atomicOr(status, 1u); break; }
+        __nanosleep(64);
+      }
+      counters[q] = 0;                        // next use of this slot is two searches away (see sharded.py)
+    }
+    __syncthreads();
+  }
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int g = e / k_in, i = e - g * k_in;
     const uint64_t* src = (ptrs ? ptrs[g] : base + (size_t)g * stride_g) + (size_t)q * k_in;
-    sk[e] = src[i];
+    sk[e] = counters ? __ldcg(src + i) : src[i];
   }
   for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
     out_scores[(size_t)q * k_out + j] = -INFINITY;
@@ -400,20 +433,21 @@ seed_select_kernel(const float* __restrict__ scores, int S, int k, uint32_t* __r
 static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan& pl, int nq, int k,
-                       uint64_t id_base, const uint32_t* gthr, uint64_t* out_keys, float* out_scores,
-                       int64_t* out_ids, const MergePush* push, cudaStream_t stream) {
+                       uint64_t id_base, const uint32_t* gthr, uint64_t* scratch, uint64_t* out_keys,
+                       float* out_scores, int64_t* out_ids, const MergePush* push, cudaStream_t stream) {
   const int VS = pl.S * pl.sets;              // candidate lists per query
   const int tmax = VS * pl.keep;
   const int PK = next_pow2(k);
   RA_REQUIRE(tmax <= 16384 && VS <= 1024 && PK <= 2048, "merge: S*sets*keep=%d too large", tmax);
-  const size_t smem = (size_t)(tmax + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(VS + 1) * 4;
+  const int smem_keys = tmax < MERGE_SMEM_KEYS ? tmax : MERGE_SMEM_KEYS;
+  const size_t smem = (size_t)(smem_keys + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(VS + 1) * 4;
   RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (16384 + 2048) * 8 + 1025 * 4));
-  MergePush mp{nullptr, 0, 1};
+                               (MERGE_SMEM_KEYS + 2048) * 8 + 1025 * 4));
+  MergePush mp{nullptr, 0, 1, 0};
   if (push) mp = *push;
-  merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, pl.MB, VS, pl.sets, pl.rows_per_item,
-                                                         pl.cap, k, PK, tmax, id_base, gthr, out_keys, out_scores,
-                                                         out_ids, mp);
+  merge_lists_kernel<<<nq, MERGE_LISTS_THREADS, smem, stream>>>(lists, counts, pl.MB, VS, pl.sets, pl.rows_per_item,
+                                                               pl.cap, k, PK, tmax, smem_keys, scratch, id_base, gthr,
+                                                               out_keys, out_scores, out_ids, mp);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
@@ -432,7 +466,9 @@ int launch_seed_select(const float* seed_scores, int nq, int seed_rows, int k, u
 using namespace ragarc;
 
 static int merge_sorted_launch(const uint64_t* base, size_t stride_g, const uint64_t* const* ptrs, int nlists,
-                               int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream) {
+                               int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream,
+                               uint32_t* counters = nullptr, uint32_t expected = 0, long long timeout_cycles = 0,
+                               uint32_t* status = nullptr) {
   RA_REQUIRE(out_scores && out_ids, "merge_topk_keys: null pointer");
   RA_REQUIRE(nlists > 0 && nq >= 0 && k_in > 0 && k_out > 0 && k_out <= nlists * k_in,
              "merge_topk_keys: bad shape G=%d nq=%d k_in=%d k_out=%d", nlists, nq, k_in, k_out);
@@ -442,7 +478,8 @@ static int merge_sorted_launch(const uint64_t* base, size_t stride_g, const uint
   if (smem > 48 * 1024)
     RA_CUDA(cudaFuncSetAttribute(merge_sorted_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_sorted_keys_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(base, stride_g, ptrs, nlists, nq, k_in, k_out,
-                                                                   out_scores, out_ids);
+                                                                   out_scores, out_ids, counters, expected,
+                                                                   timeout_cycles, status);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }
@@ -457,4 +494,15 @@ extern "C" int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int n
                                           float* out_scores, int64_t* out_ids, void* stream) {
   RA_REQUIRE(key_ptrs, "merge_topk_keys_p2p: null pointer table");
   return merge_sorted_launch(nullptr, 0, key_ptrs, nlists, nq, k_in, k_out, out_scores, out_ids, stream);
+}
+
+extern "C" int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int k_in, int k_out,
+                                       float* out_scores, int64_t* out_ids, double timeout_ms,
+                                       uint32_t* status, void* stream) {
+  RA_REQUIRE(inbox, "merge_topk_inbox: null inbox");
+  RA_REQUIRE(n_ranks > 0 && nq_per_rank > 0 && k_in > 0, "merge_topk_inbox: bad shape");
+  uint32_t* counters = reinterpret_cast<uint32_t*>(inbox + (size_t)n_ranks * nq_per_rank * k_in);
+  const long long cycles = (long long)((timeout_ms > 0 ? timeout_ms : 2000.0) * 1.5e6);   // ~1.5 GHz worst case
+  return merge_sorted_launch(inbox, (size_t)nq_per_rank * k_in, nullptr, n_ranks, nq_per_rank, k_in, k_out,
+                             out_scores, out_ids, stream, counters, (uint32_t)n_ranks, cycles, status);
 }

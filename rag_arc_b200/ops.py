@@ -206,11 +206,12 @@ def dense_topk_keys(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base
 
 
 def dense_topk_keys_push(corpus: torch.Tensor, queries: torch.Tensor, k: int, id_base: int,
-                         inbox_table: torch.Tensor, rank: int, nq_per_rank: int, *,
+                         inbox_table: torch.Tensor, rank: int, nq_per_rank: int, *, signal: bool = False,
                          n_rows: Optional[int] = None, path: int = N.DENSE_AUTO) -> None:
     """Per-shard search whose sorted key rows go straight into the inbox of the rank owning each
     query (``inbox_table``: int64 device tensor of one ``[n_ranks, nq_per_rank, k]`` inbox pointer per
-    rank, local or peer memory) - the producer half of the query-owner exchange."""
+    rank, local or peer memory) - the producer half of the query-owner exchange.  ``signal``: also
+    bump the owner's per-query arrival counters behind the inbox (see ``merge_topk_inbox``)."""
     _cuda(corpus, "corpus"); _cuda(queries, "queries"); _cuda(inbox_table, "inbox_table")
     n = corpus.shape[0] if n_rows is None else int(n_rows)
     d = corpus.shape[1]
@@ -221,8 +222,29 @@ def dense_topk_keys_push(corpus: torch.Tensor, queries: torch.Tensor, k: int, id
     with torch.cuda.device(dev):
         N.check(N.lib.ragarc_dense_topk_keys_push(corpus.data_ptr(), n, d, code, queries.data_ptr(), nq, k,
                                                   int(id_base), inbox_table.data_ptr(), inbox_table.numel(),
-                                                  int(rank), int(nq_per_rank), ws.data_ptr(), ws.numel(),
-                                                  path, None, _stream_ptr(dev)), "dense_topk_keys_push")
+                                                  int(rank), int(nq_per_rank), int(bool(signal)), ws.data_ptr(),
+                                                  ws.numel(), path, None, _stream_ptr(dev)), "dense_topk_keys_push")
+
+
+def inbox_words(n_ranks: int, nq_per_rank: int, k: int) -> int:
+    """int64 words of one signalled inbox: the key block + one uint32 arrival counter per owned query."""
+    return n_ranks * nq_per_rank * k + (nq_per_rank + 1) // 2
+
+
+def merge_topk_inbox(inbox: torch.Tensor, n_ranks: int, nq_per_rank: int, k_in: int, k_out: int,
+                     status: Optional[torch.Tensor] = None, timeout_ms: float = 2000.0):
+    """Owner half of the signalled exchange: waits (inside the kernel, per query) until all ``n_ranks``
+    rows of a query have arrived in ``inbox`` (int64 ``[inbox_words]``), then merges them."""
+    _cuda(inbox, "inbox")
+    dev = inbox.device
+    scores = torch.empty((nq_per_rank, k_out), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq_per_rank, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_merge_topk_inbox(inbox.data_ptr(), n_ranks, nq_per_rank, k_in, k_out, scores.data_ptr(),
+                                              ids.data_ptr(), float(timeout_ms),
+                                              status.data_ptr() if status is not None else None, _stream_ptr(dev)),
+                "merge_topk_inbox")
+    return scores, ids
 
 
 def merge_topk_keys(keys: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -63,10 +63,15 @@ class _PeerExchange:
 class _OwnerExchange:
     """Query-owner exchange for one (nq, k) shape: rank g owns queries ``[g*nq_per, (g+1)*nq_per)``;
     every rank's merge kernel PUSHES the sorted key row of each query into its owner's inbox
-    (symmetric memory, stores over NVLink), one device-side barrier orders the stores, and every
-    rank merges only the ``world`` lists of its own queries out of local memory.  Compared with
-    every rank merging all ``nq`` queries from peer memory this divides the cross-shard merge work
-    by ``world`` and turns remote loads (a round trip each) into fire-and-forget stores."""
+    (symmetric memory, stores over NVLink) and bumps the owner's arrival counter of that query; the
+    owner's merge kernel waits per query for ``world`` arrivals and merges the ``world`` lists of its
+    own queries out of local memory.  Compared with every rank merging all ``nq`` queries from peer
+    memory this divides the cross-shard merge work by ``world``, turns remote loads (a round trip each)
+    into fire-and-forget stores, and needs neither a collective nor a barrier kernel between the two
+    launches (``RAGARC_OWNER_BARRIER=1`` selects the barrier-ordered variant for comparison).
+    Two inboxes alternate: a rank can be at most one search ahead of the slowest rank, because its
+    own merge of search i+1 needs that rank's rows of search i+1, which are only pushed after that
+    rank has finished merging search i."""
 
     def __init__(self, nq: int, k: int, device, group):
         import torch.distributed._symmetric_memory as symm_mem
@@ -76,24 +81,36 @@ class _OwnerExchange:
         self.nq_per = (nq + self.world - 1) // self.world
         self.q_lo = min(nq, self.rank * self.nq_per)
         self.q_hi = min(nq, self.q_lo + self.nq_per)
-        self.inbox = symm_mem.empty((2, self.world, self.nq_per, k), dtype=torch.int64, device=device)
+        self.signalled = os.environ.get("RAGARC_OWNER_BARRIER", "0") != "1"
+        self.words = ops.inbox_words(self.world, self.nq_per, k)
+        self.inbox = symm_mem.empty((2, self.words), dtype=torch.int64, device=device)
         self.inbox.zero_()
         self.hdl = symm_mem.rendezvous(self.inbox, grp)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        slot_bytes = self.world * self.nq_per * k * 8
-        self.tables = [torch.tensor([p + s * slot_bytes for p in ptrs], dtype=torch.int64, device=device)
+        self.tables = [torch.tensor([p + s * self.words * 8 for p in ptrs], dtype=torch.int64, device=device)
                        for s in range(2)]
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
         self.step = 0
         torch.cuda.synchronize(device)
         dist.barrier(group=grp)                      # every inbox is zeroed before anybody pushes
 
+    def timed_out(self) -> bool:
+        """True if a merge kernel gave up waiting for a peer's rows since the last call (synchronises)."""
+        bad = bool(int(self.status.item()) != 0)
+        self.status.zero_()
+        return bad
+
     def push_and_merge(self, push, k_out: int):
         slot = self.step & 1
         self.step += 1
-        push(self.tables[slot])                      # this rank's key rows -> the owners' inboxes
-        self.hdl.barrier(channel=slot)               # all rows of this search have landed
-        scores, rows = ops.merge_topk_keys(self.inbox[slot], k_out)
+        push(self.tables[slot], self.signalled)      # this rank's key rows -> the owners' inboxes
         n_own = self.q_hi - self.q_lo
+        if self.signalled:
+            scores, rows = ops.merge_topk_inbox(self.inbox[slot], self.world, self.nq_per, self.k, k_out, self.status)
+        else:
+            self.hdl.barrier(channel=slot)           # all rows of this search have landed
+            keys = self.inbox[slot][:self.world * self.nq_per * self.k].view(self.world, self.nq_per, self.k)
+            scores, rows = ops.merge_topk_keys(keys, k_out)
         return scores[:n_own], rows[:n_own]
 
 
@@ -173,10 +190,10 @@ class ShardedFlatIndex:
                 s, r = self.search(queries, k)
                 return s[lo:hi], r[lo:hi]
             self._owner[(nq, k)] = ox
-        self.exchange_used = "owner-push"
+        self.exchange_used = "owner-push" if ox.signalled else "owner-push+barrier"
         return ox.push_and_merge(
-            lambda table: ops.dense_topk_keys_push(self.rows, queries, k, self.id_base, table, self.rank,
-                                                   ox.nq_per, n_rows=self.n_local), k)
+            lambda table, signal: ops.dense_topk_keys_push(self.rows, queries, k, self.id_base, table, self.rank,
+                                                           ox.nq_per, signal=signal, n_rows=self.n_local), k)
 
     def capture(self, queries: torch.Tensor, k: int, owned: bool = False):
         """CUDA-graph the whole search (scoring, key exchange, merge) for a fixed query buffer:

@@ -139,29 +139,42 @@ def test_keys_and_merge_equal_single_shot(dev):
     assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
 
 
+@pytest.mark.parametrize("signal", [False, True])
 @pytest.mark.parametrize("n,nq,k,G", [(50_000, 33, 20, 3), (200_000, 520, 100, 4), (1_000, 5, 10, 8)])
-def test_query_owner_push_exchange_equals_single_shot(dev, n, nq, k, G):
+def test_query_owner_push_exchange_equals_single_shot(dev, n, nq, k, G, signal):
     """The multi-GPU query-owner exchange on one device: G row shards, every shard's merge kernel
     pushes the key row of query q into the inbox of rank q // nq_per (here: G inboxes in local
     memory), every owner merges its own queries - concatenated, the owners' results must be bitwise
-    the single-shot result."""
+    the single-shot result.  signal=True: the pushers count themselves into per-query arrival counters
+    behind each inbox and the owner's merge kernel waits on them (no barrier between the kernels);
+    run twice to check that the counters are reset."""
     d = 128
     x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev, seed=21)
     q, _ = synth.dense_queries_cuda(x, nq, seed=22)
     s_ref, i_ref = ops.dense_topk(x, q, k)
     nq_per = (nq + G - 1) // G
-    inbox = torch.zeros((G, G, nq_per, k), dtype=torch.int64, device=dev)      # [owner][source rank][query][k]
+    words = ops.inbox_words(G, nq_per, k)
+    inbox = torch.zeros((G, words), dtype=torch.int64, device=dev)             # [owner][keys | counters]
     table = torch.tensor([inbox[o].data_ptr() for o in range(G)], dtype=torch.int64, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
     per = (n + G - 1) // G
-    for g in range(G):
-        lo, hi = min(n, g * per), min(n, (g + 1) * per)
-        ops.dense_topk_keys_push(x[lo:hi].contiguous(), q, k, lo, table, g, nq_per)
-    outs_s, outs_i = [], []
-    for o in range(G):
-        s, i = ops.merge_topk_keys(inbox[o], k)
-        n_own = max(0, min(nq, (o + 1) * nq_per) - o * nq_per)
-        outs_s.append(s[:n_own]); outs_i.append(i[:n_own])
-    assert torch.equal(torch.cat(outs_i), i_ref) and torch.equal(torch.cat(outs_s), s_ref)
+    for rep in range(2 if signal else 1):
+        for g in range(G):
+            lo, hi = min(n, g * per), min(n, (g + 1) * per)
+            ops.dense_topk_keys_push(x[lo:hi].contiguous(), q, k, lo, table, g, nq_per, signal=signal)
+        outs_s, outs_i = [], []
+        for o in range(G):
+            if signal:
+                s, i = ops.merge_topk_inbox(inbox[o], G, nq_per, k, k, status, timeout_ms=200.0)
+            else:
+                s, i = ops.merge_topk_keys(inbox[o][:G * nq_per * k].view(G, nq_per, k), k)
+            n_own = max(0, min(nq, (o + 1) * nq_per) - o * nq_per)
+            outs_s.append(s[:n_own]); outs_i.append(i[:n_own])
+        assert torch.equal(torch.cat(outs_i), i_ref) and torch.equal(torch.cat(outs_s), s_ref)
+        assert int(status.item()) == 0
+        if signal:      # every counter was consumed and reset
+            cnt = inbox[:, G * nq_per * k:].view(torch.int32)
+            assert int(cnt.abs().sum()) == 0
 
 
 def test_published_rung_thresholds_do_not_change_results(dev):

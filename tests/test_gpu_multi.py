@@ -76,7 +76,7 @@ def _owner_worker(rank, world, port, out):
     for it in range(4):                                                     # both inbox slots, twice
         s, i = idx.search_owned(q, k)
         ok = ok and bool(torch.equal(i, i_ref[qlo:qhi]) and torch.equal(s, s_ref[qlo:qhi]))
-    ok = ok and idx.exchange_used == "owner-push"
+    ok = ok and idx.exchange_used == "owner-push" and not idx._owner[(nq, k)].timed_out()
     replay, s, i = idx.capture(q, k, owned=True)
     for it in range(3):
         s, i = replay()
