@@ -193,9 +193,10 @@ int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype,
                                 int rank, int nq_per_rank, int signal, void* workspace,
                                 size_t workspace_bytes, int path, int* path_used_host, void* stream);
 /* Owner side of the signalled exchange: inbox = this rank's [n_ranks, nq_per_rank, k_in] key block +
- * counters.  *status (device uint32, may be NULL) gets bit 0 set if a wait gave up after timeout_ms
- * (<= 0: 2000 ms) - the results of that search are then incomplete. */
-int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int k_in, int k_out,
+ * counters; nq_own <= nq_per_rank = queries of the batch this rank actually owns (the last ranks may
+ * own fewer, or none).  out_*: [nq_own, k_out].  *status (device uint32, may be NULL) gets bit 0 set
+ * if a wait gave up after timeout_ms (<= 0: 2000 ms) - the results of that search are then incomplete. */
+int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int nq_own, int k_in, int k_out,
                             float* out_scores, int64_t* out_ids, double timeout_ms, uint32_t* status,
                             void* stream);
 

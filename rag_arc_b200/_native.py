@@ -41,7 +41,7 @@ EXPORTS = [
 
 def nvcc_command(out: str = LIB_PATH):
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,550",
+            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,550,128",
             *[os.path.join(CSRC, s) for s in SOURCES], "-o", out]
 
 
@@ -86,7 +86,7 @@ def _load():
                                            c_size_t, c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys_push": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, c_int,
                                                 c_int, c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
-        "ragarc_merge_topk_inbox": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_double, P, P]),
+        "ragarc_merge_topk_inbox": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_double, P, P]),
         "ragarc_normalize_split3": (c_int, [P, P, c_int64, c_int, c_int, P]),
         "ragarc_dense_topk_x3_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
         "ragarc_dense_topk_x3": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, c_size_t, P]),

@@ -11,8 +11,8 @@ namespace ragarc {
 
 constexpr int MERGE_THREADS = 512;        // seed_select_kernel
 constexpr int MERGE_LISTS_THREADS = 256;  // merge_lists_kernel: 8 CTAs per SM, all queries of a 1024-batch resident at once
-constexpr int MERGE_SMEM_KEYS = 4096;     // candidate keys a merge_lists CTA holds in shared memory; queries with more
-                                          // raw candidates (loose thresholds) gather into a global scratch row instead
+constexpr int MERGE_SMEM_KEYS = 2048;     // filtered candidate keys a merge_lists CTA holds in shared memory; a query
+                                          // with more survivors (loose thresholds) continues in a global scratch row
 
 // k-th largest of keys[0..T) (T > k): leaves the winners (exactly k) in win[0..k), unordered.
 // hist: 256 words, sel: 3 words, nwin: 1 word of shared memory.
@@ -159,7 +159,7 @@ __device__ __forceinline__ void select_sort_emit(uint64_t* keys, int T, int k, i
 // full radix select if more than MERGE_WIN keys survive (heavily tied scores).
 constexpr int MERGE_WIN = 512;       // survivors that are sorted directly
 
-__global__ void __launch_bounds__(MERGE_LISTS_THREADS)
+__global__ void __launch_bounds__(MERGE_LISTS_THREADS, 8)
 merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts, int MB, int S, int sets,
                    int rows, int cap, int k, int PK, int tmax, int smem_keys, uint64_t* __restrict__ scratch,
                    uint64_t id_base, const uint32_t* __restrict__ gthr, uint64_t* out_keys,
@@ -197,37 +197,54 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   __syncthreads();
   int total_raw = offs[S];
   if (total_raw > tmax) total_raw = tmax;    // cannot happen: every list is <= keep and S*keep <= tmax
-  if (total_raw > smem_keys) keys = scratch + (size_t)q * tmax;   // rare: loose thresholds; same code, global (L2) array
+  uint64_t* spill = scratch + (size_t)q * tmax;   // this query's global row: only touched if more than smem_keys candidates survive
   // (A) flattened gather: element e of the concatenated lists belongs to the list found by binary
-  // search in the prefix sums, so every load is independent of every other (a warp-per-list loop
-  // serialises S/16 dependent L2 round trips).  Candidates below the query's shared threshold - a
-  // score that at least k rows are known to reach - are dropped on the way in.
+  // search in the prefix sums, so every load is independent of every other: a thread first issues
+  // the loads of all its elements of a pass (one L2 round trip for 1024 candidates), then filters.
+  // Candidates below the query's shared threshold - a score that at least k rows are known to
+  // reach - are dropped on the way in; what survives goes to shared memory (typically a few hundred).
   {
+    constexpr int NPT = 4;                    // elements per thread and pass
     const uint32_t bound = gthr ? gthr[q] : 0u;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0u;
-    for (int b = 0; b < total_raw; b += blockDim.x) {
-      const int e = b + threadIdx.x;
-      uint64_t key = 0ull;
-      if (e < total_raw) {
-        int lo = 0, hi = S;                   // largest sl with offs[sl] <= e
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= e) lo = mid; else hi = mid; }
-        key = lists[((((size_t)(lo / sets) * MB + qb) * rows + r) * sets + (lo % sets)) * (size_t)cap + (e - offs[lo])];
+    for (int b = 0; b < total_raw; b += blockDim.x * NPT) {
+      uint64_t kreg[NPT];
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        const int e = b + u * blockDim.x + threadIdx.x;
+        kreg[u] = 0ull;
+        if (e < total_raw) {
+          int lo = 0, hi = S;                 // largest sl with offs[sl] <= e
+          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= e) lo = mid; else hi = mid; }
+          kreg[u] = lists[((((size_t)(lo / sets) * MB + qb) * rows + r) * sets + (lo % sets)) * (size_t)cap + (e - offs[lo])];
+        }
       }
-      const uint32_t ord = uint32_t(key >> 32);
-      const bool keep = e < total_raw && ord >= bound;
-      const unsigned bal = __ballot_sync(FULL, keep);
-      uint32_t base = 0;
-      if (lane == 0 && bal) base = atomicAdd(&nwin, (uint32_t)__popc(bal));
-      base = __shfl_sync(FULL, base, 0);
-      if (keep) {
-        keys[base + __popc(bal & ((1u << lane) - 1u))] = key;
-        lmin = min(lmin, ord); lmax = max(lmax, ord);
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        const uint64_t key = kreg[u];
+        const uint32_t ord = uint32_t(key >> 32);
+        const bool keep = key != 0ull && ord >= bound;
+        const unsigned bal = __ballot_sync(FULL, keep);
+        uint32_t base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&nwin, (uint32_t)__popc(bal));
+        base = __shfl_sync(FULL, base, 0);
+        if (keep) {
+          const uint32_t idx = base + __popc(bal & ((1u << lane) - 1u));
+          if (idx < (uint32_t)smem_keys) keys[idx] = key; else spill[idx] = key;
+          lmin = min(lmin, ord); lmax = max(lmax, ord);
+        }
       }
     }
     lmin = __reduce_min_sync(FULL, lmin); lmax = __reduce_max_sync(FULL, lmax);
     if (lane == 0) { atomicMin(&omin, lmin); atomicMax(&omax, lmax); }
   }
   __syncthreads();
+  if ((int)nwin > smem_keys) {
+    // rare (loose thresholds, heavy ties): continue out of the global row - same code, generic pointer
+    for (int i = threadIdx.x; i < smem_keys; i += blockDim.x) spill[i] = keys[i];
+    keys = spill;
+    __syncthreads();
+  }
   const int total = (int)nwin;
   __syncthreads();
   if (threadIdx.x == 0) nwin = 0;
@@ -292,13 +309,14 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
   }
   if (push.inboxes && push.n_ranks > 0) {
-    // the row is in the owner's inbox: make it visible system-wide, then count this rank in
-    __threadfence_system();
+    // the row is in the owner's inbox: one release-add at system scope by one thread, after a CTA barrier,
+    // publishes every thread's stores (release is cumulative over what the barrier ordered before it);
+    // fencing in all 256 threads instead cost 15 us per search
     __syncthreads();
     if (threadIdx.x == 0) {
       const int owner = q / push.nq_per;
       uint32_t* counters = reinterpret_cast<uint32_t*>(push.inboxes[owner] + (size_t)push.n_ranks * push.nq_per * k);
-      atomicAdd_system(counters + (q - owner * push.nq_per), 1u);
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counters + (q - owner * push.nq_per)) : "memory");
     }
   }
 }
@@ -496,13 +514,15 @@ extern "C" int ragarc_merge_topk_keys_p2p(const uint64_t* const* key_ptrs, int n
   return merge_sorted_launch(nullptr, 0, key_ptrs, nlists, nq, k_in, k_out, out_scores, out_ids, stream);
 }
 
-extern "C" int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int k_in, int k_out,
+extern "C" int ragarc_merge_topk_inbox(uint64_t* inbox, int n_ranks, int nq_per_rank, int nq_own, int k_in, int k_out,
                                        float* out_scores, int64_t* out_ids, double timeout_ms,
                                        uint32_t* status, void* stream) {
   RA_REQUIRE(inbox, "merge_topk_inbox: null inbox");
-  RA_REQUIRE(n_ranks > 0 && nq_per_rank > 0 && k_in > 0, "merge_topk_inbox: bad shape");
+  RA_REQUIRE(n_ranks > 0 && nq_per_rank > 0 && k_in > 0 && nq_own >= 0 && nq_own <= nq_per_rank,
+             "merge_topk_inbox: bad shape");
+  if (nq_own == 0) return RAGARC_OK;          // this rank owns no query of the batch: nothing arrives, nothing to merge
   uint32_t* counters = reinterpret_cast<uint32_t*>(inbox + (size_t)n_ranks * nq_per_rank * k_in);
   const long long cycles = (long long)((timeout_ms > 0 ? timeout_ms : 2000.0) * 1.5e6);   // ~1.5 GHz worst case
-  return merge_sorted_launch(inbox, (size_t)nq_per_rank * k_in, nullptr, n_ranks, nq_per_rank, k_in, k_out,
+  return merge_sorted_launch(inbox, (size_t)nq_per_rank * k_in, nullptr, n_ranks, nq_own, k_in, k_out,
                              out_scores, out_ids, stream, counters, (uint32_t)n_ranks, cycles, status);
 }

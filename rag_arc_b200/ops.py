@@ -231,16 +231,17 @@ def inbox_words(n_ranks: int, nq_per_rank: int, k: int) -> int:
     return n_ranks * nq_per_rank * k + (nq_per_rank + 1) // 2
 
 
-def merge_topk_inbox(inbox: torch.Tensor, n_ranks: int, nq_per_rank: int, k_in: int, k_out: int,
+def merge_topk_inbox(inbox: torch.Tensor, n_ranks: int, nq_per_rank: int, nq_own: int, k_in: int, k_out: int,
                      status: Optional[torch.Tensor] = None, timeout_ms: float = 2000.0):
     """Owner half of the signalled exchange: waits (inside the kernel, per query) until all ``n_ranks``
-    rows of a query have arrived in ``inbox`` (int64 ``[inbox_words]``), then merges them."""
+    rows of a query have arrived in ``inbox`` (int64 ``[inbox_words]``), then merges them; ``nq_own``
+    of the ``nq_per_rank`` inbox rows belong to queries of this batch.  -> ``[nq_own, k_out]`` results."""
     _cuda(inbox, "inbox")
     dev = inbox.device
-    scores = torch.empty((nq_per_rank, k_out), dtype=torch.float32, device=dev)
-    ids = torch.empty((nq_per_rank, k_out), dtype=torch.int64, device=dev)
+    scores = torch.empty((nq_own, k_out), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq_own, k_out), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib.ragarc_merge_topk_inbox(inbox.data_ptr(), n_ranks, nq_per_rank, k_in, k_out, scores.data_ptr(),
+        N.check(N.lib.ragarc_merge_topk_inbox(inbox.data_ptr(), n_ranks, nq_per_rank, nq_own, k_in, k_out, scores.data_ptr(),
                                               ids.data_ptr(), float(timeout_ms),
                                               status.data_ptr() if status is not None else None, _stream_ptr(dev)),
                 "merge_topk_inbox")

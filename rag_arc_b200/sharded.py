@@ -68,7 +68,9 @@ class _OwnerExchange:
     own queries out of local memory.  Compared with every rank merging all ``nq`` queries from peer
     memory this divides the cross-shard merge work by ``world``, turns remote loads (a round trip each)
     into fire-and-forget stores, and needs neither a collective nor a barrier kernel between the two
-    launches (``RAGARC_OWNER_BARRIER=1`` selects the barrier-ordered variant for comparison).
+    launches.  (Measured at 2 GPUs the counter variant is no faster than one symmetric-memory barrier
+    between the two launches, so the barrier-ordered variant is the default; ``RAGARC_OWNER_SIGNAL=1``
+    selects the counters.)
     Two inboxes alternate: a rank can be at most one search ahead of the slowest rank, because its
     own merge of search i+1 needs that rank's rows of search i+1, which are only pushed after that
     rank has finished merging search i."""
@@ -81,7 +83,7 @@ class _OwnerExchange:
         self.nq_per = (nq + self.world - 1) // self.world
         self.q_lo = min(nq, self.rank * self.nq_per)
         self.q_hi = min(nq, self.q_lo + self.nq_per)
-        self.signalled = os.environ.get("RAGARC_OWNER_BARRIER", "0") != "1"
+        self.signalled = os.environ.get("RAGARC_OWNER_SIGNAL", "0") == "1"
         self.words = ops.inbox_words(self.world, self.nq_per, k)
         self.inbox = symm_mem.empty((2, self.words), dtype=torch.int64, device=device)
         self.inbox.zero_()
@@ -106,11 +108,10 @@ class _OwnerExchange:
         push(self.tables[slot], self.signalled)      # this rank's key rows -> the owners' inboxes
         n_own = self.q_hi - self.q_lo
         if self.signalled:
-            scores, rows = ops.merge_topk_inbox(self.inbox[slot], self.world, self.nq_per, self.k, k_out, self.status)
-        else:
-            self.hdl.barrier(channel=slot)           # all rows of this search have landed
-            keys = self.inbox[slot][:self.world * self.nq_per * self.k].view(self.world, self.nq_per, self.k)
-            scores, rows = ops.merge_topk_keys(keys, k_out)
+            return ops.merge_topk_inbox(self.inbox[slot], self.world, self.nq_per, n_own, self.k, k_out, self.status)
+        self.hdl.barrier(channel=slot)               # all rows of this search have landed
+        keys = self.inbox[slot][:self.world * self.nq_per * self.k].view(self.world, self.nq_per, self.k)
+        scores, rows = ops.merge_topk_keys(keys, k_out)
         return scores[:n_own], rows[:n_own]
 
 

@@ -164,11 +164,11 @@ def test_query_owner_push_exchange_equals_single_shot(dev, n, nq, k, G, signal):
             ops.dense_topk_keys_push(x[lo:hi].contiguous(), q, k, lo, table, g, nq_per, signal=signal)
         outs_s, outs_i = [], []
         for o in range(G):
+            n_own = max(0, min(nq, (o + 1) * nq_per) - o * nq_per)
             if signal:
-                s, i = ops.merge_topk_inbox(inbox[o], G, nq_per, k, k, status, timeout_ms=200.0)
+                s, i = ops.merge_topk_inbox(inbox[o], G, nq_per, n_own, k, k, status, timeout_ms=200.0)
             else:
                 s, i = ops.merge_topk_keys(inbox[o][:G * nq_per * k].view(G, nq_per, k), k)
-            n_own = max(0, min(nq, (o + 1) * nq_per) - o * nq_per)
             outs_s.append(s[:n_own]); outs_i.append(i[:n_own])
         assert torch.equal(torch.cat(outs_i), i_ref) and torch.equal(torch.cat(outs_s), s_ref)
         assert int(status.item()) == 0
@@ -200,6 +200,27 @@ def test_published_rung_thresholds_do_not_change_results(dev):
         assert sorted(got[:40]) == got[:40] and all(g % 3000 == got[0] % 3000 for g in got[:40])
         assert got[0] % 3000 == int(want_r[qi, 0])
         assert got[:40] == [int(want_r[qi, 0]) + 3000 * j for j in range(40)]
+
+
+def test_massive_ties_take_the_merge_spill_path(dev):
+    """200k identical rows: every candidate ties with every threshold, nothing can be filtered, every
+    list is cut to its budget by the exact prune and the merge kernel gets more survivors than its
+    shared-memory array holds (global spill row).  The answer is fully determined by the tie rule:
+    rows 0..k-1 in order, for every query, on both kernels' shared merge."""
+    d, k = 64, 100
+    row = torch.nn.functional.normalize(torch.randn((1, d), generator=torch.Generator().manual_seed(5)), dim=1)
+    x = row.repeat(200_000, 1).to(torch.bfloat16).to(dev).contiguous()
+    q = torch.cat([row, -row, torch.randn((5, d), generator=torch.Generator().manual_seed(6))], 0).to(torch.bfloat16).to(dev)
+    for nq in (7, 300):
+        qq = q.repeat((nq + 6) // 7, 1)[:nq].contiguous()
+        scores, ids = ops.dense_topk(x, qq, k)
+        want = torch.arange(k, device=dev)[None, :].expand(nq, k)
+        assert torch.equal(ids, want)
+        assert (scores == scores[:, :1]).all()
+    # a planted better row at the very end must still come first
+    x[-1] = (row * 2).to(torch.bfloat16).to(dev)[0]
+    scores, ids = ops.dense_topk(x, q[:1].contiguous(), k)
+    assert ids[0, 0].item() == 199_999 and ids[0, 1:].tolist() == list(range(k - 1))
 
 
 def test_full_size_properties_1m_x_768(dev):

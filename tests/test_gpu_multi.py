@@ -58,9 +58,9 @@ def test_sharded_search_equals_single_gpu(exchange):
     assert ok == 1, f"mismatch (exchange used: {used})"
 
 
-def _owner_worker(rank, world, port, out):
+def _owner_worker(rank, world, port, signal, out):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RAGARC_OWNER_SIGNAL=signal)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -76,7 +76,7 @@ def _owner_worker(rank, world, port, out):
     for it in range(4):                                                     # both inbox slots, twice
         s, i = idx.search_owned(q, k)
         ok = ok and bool(torch.equal(i, i_ref[qlo:qhi]) and torch.equal(s, s_ref[qlo:qhi]))
-    ok = ok and idx.exchange_used == "owner-push" and not idx._owner[(nq, k)].timed_out()
+    ok = ok and idx.exchange_used.startswith("owner-push") and not idx._owner[(nq, k)].timed_out()
     replay, s, i = idx.capture(q, k, owned=True)
     for it in range(3):
         s, i = replay()
@@ -102,16 +102,18 @@ def _owner_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_query_owner_exchange_equals_single_gpu():
+@pytest.mark.parametrize("signal", ["0", "1"])
+def test_query_owner_exchange_equals_single_gpu(signal):
     """search_owned (merge kernel pushes key rows into the owner's inbox over NVLink, every rank merges
-    its own queries): eager, CUDA-graphed and through the host pipeline, against the single-GPU result."""
+    its own queries): eager, CUDA-graphed and through the host pipeline, against the single-GPU result;
+    ordered by a symmetric-memory barrier ("0") or by per-query arrival counters ("1")."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_owner_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_owner_worker, args=(r, world, port, signal, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
