@@ -46,8 +46,9 @@ enum { RAGARC_F32 = 0, RAGARC_BF16 = 1, RAGARC_F16 = 2, RAGARC_F64 = 3 /* adjace
 /* pooling modes (sentence-transformers Pooling module) */
 enum { RAGARC_POOL_MEAN = 0, RAGARC_POOL_CLS = 1, RAGARC_POOL_LAST = 2 };
 
-/* similarity of a ragarc_index_t: raw inner product, or cosine (rows and queries L2-normalised) */
-enum { RAGARC_METRIC_IP = 0, RAGARC_METRIC_COSINE = 1 };
+/* similarity of a ragarc_index_t: raw inner product, cosine (rows and queries L2-normalised), or
+ * squared L2 distance (results ascending, like faiss.IndexFlatL2) */
+enum { RAGARC_METRIC_IP = 0, RAGARC_METRIC_COSINE = 1, RAGARC_METRIC_L2 = 2 };
 
 /* which dense scoring kernel ran / should run */
 enum { RAGARC_DENSE_AUTO = 0, RAGARC_DENSE_SIMT = 1, RAGARC_DENSE_TCGEN05 = 2 };
@@ -152,6 +153,23 @@ int ragarc_sharded_add(ragarc_sharded_index_t* index, const float* rows_host, in
 int ragarc_sharded_search(ragarc_sharded_index_t* index, const float* queries_host, int nq, int k,
                           float* out_scores_host, int64_t* out_ids_host);
 int64_t ragarc_sharded_ntotal(const ragarc_sharded_index_t* index);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact squared-L2 search.   Replaces faiss.IndexFlatL2 (VectorStore_Faiss.py:125-126 metric "l2";
+ *   search at :263 returns squared distances ascending) on the SAME scoring + selection kernels:
+ *   ||q - x||^2 = ||q||^2 - 2 (q.x - ||x||^2/2).  ragarc_l2_augment stores a row as [x | -||x||^2/2]
+ *   (half precision: the extra term as three pieces h1+h2+h3, padded with zeros to a multiple of 8
+ *   columns) and a query as [q | 1] ([q | 1 1 1 0..]); ragarc_dense_topk over the augmented matrices
+ *   (width ragarc_l2_aug_dim(d, dtype)) ranks nearest first; ragarc_l2_distances turns the k kept
+ *   values into distances in place (clamped at 0, +inf for -1 padding).  ||x||^2 is taken over the
+ *   stored (rounded) values.  sqnorm_out (may be NULL): fp32 [n] squared norms.
+ *   normalize != 0 applies faiss.normalize_L2 first (the reference's normalize_L2 flag, :150-154).
+ */
+int ragarc_l2_aug_dim(int d, int dtype);
+int ragarc_l2_augment(const float* src, void* dst, int64_t n, int d, int dst_dtype, int is_query,
+                      int normalize, float* sqnorm_out, void* stream);
+int ragarc_l2_distances(float* scores, const void* queries_aug, int dtype, int nq, int k, int d,
+                        void* stream);
 
 /* fp32-accurate search on the tensor cores ("bf16x3").  An fp32 vector v is stored as three bf16
  * planes v1+v2+v3 (v1 = bf16(v), v2 = bf16(v-v1), v3 = bf16(v-v1-v2); exact to 2^-24 relative), a

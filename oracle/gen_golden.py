@@ -40,6 +40,41 @@ class TableEmbeddings:
         return self.table[text].tolist()
 
 
+def gen_dense_l2(ns):
+    """Metric "l2" of the reference's FaissVectorStore (IndexFlatL2 behind it, squared distances
+    ascending, _euclidean_relevance_score_fn) over the vectors of dense_small.npz."""
+    import warnings
+    z = np.load(os.path.join(GOLD, "dense_small.npz"))
+    with open(os.path.join(GOLD, "dense_small.json")) as f:
+        base = json.load(f)
+    texts, queries = base["texts"], base["queries"]
+    table = {t: v for t, v in zip(texts, z["vecs"])}
+    table.update({t: v for t, v in zip(queries, z["qvecs"])})
+    table["test"] = np.zeros(z["vecs"].shape[1], np.float32)
+    emb = TableEmbeddings(table)
+    out = {"source": "FaissVectorStore(metric='l2') executed live over oracle.dense.IndexFlatL2", "cases": []}
+    for normalize in (False, True):
+        store = ns.FaissVectorStore.from_texts(texts, emb, ids=[str(i) for i in range(len(texts))], metric="l2",
+                                               normalize_L2=normalize)
+        for k in (1, 4, 10):
+            for qi, qt in enumerate(queries):
+                res = store.similarity_search_with_score(qt, k)
+                out["cases"].append({"kind": "similarity_with_score", "normalize_L2": normalize, "k": k, "query": qi,
+                                     "ids": [int(doc.id) for doc, _ in res], "scores": [float(s) for _, s in res]})
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for qi, qt in enumerate(queries[:4]):
+                rel = store.similarity_search_with_relevance_scores(qt, k=6)
+                out["cases"].append({"kind": "relevance", "normalize_L2": normalize, "query": qi,
+                                     "ids": [int(d_.id) for d_, _ in rel], "relevance": [float(s) for _, s in rel]})
+        for qi, qt in enumerate(queries[:4]):
+            docs = store.max_marginal_relevance_search(qt, k=3, fetch_k=10, lambda_mult=0.5)
+            out["cases"].append({"kind": "mmr", "normalize_L2": normalize, "query": qi, "ids": [int(d_.id) for d_ in docs]})
+    with open(os.path.join(GOLD, "dense_l2_small.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    return len(out["cases"])
+
+
 def gen_rrf(ns):
     rng = np.random.default_rng(20250101)
     cases = []
@@ -242,6 +277,7 @@ def main():
     print("dense cases:", gen_dense(ns))
     print("bm25+hybrid cases:", gen_bm25_hybrid(ns))
     print("adjacent cosine pairs:", gen_adjacent_cosine(ns))
+    print("dense l2 cases:", gen_dense_l2(ns))
 
 
 if __name__ == "__main__":

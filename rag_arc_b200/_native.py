@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu"]
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
-METRIC_IP, METRIC_COSINE = 0, 1
+METRIC_IP, METRIC_COSINE, METRIC_L2 = 0, 1, 2
 POOL_MEAN, POOL_CLS, POOL_LAST = 0, 1, 2
 DENSE_AUTO, DENSE_SIMT, DENSE_TCGEN05 = 0, 1, 2
 
@@ -28,6 +28,7 @@ EXPORTS = [
     "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk_plan", "ragarc_dense_topk", "ragarc_dense_topk_keys",
     "ragarc_dense_topk_keys_push", "ragarc_merge_topk_inbox",
+    "ragarc_l2_aug_dim", "ragarc_l2_augment", "ragarc_l2_distances",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
@@ -87,6 +88,9 @@ def _load():
         "ragarc_dense_topk_keys_push": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, c_int,
                                                 c_int, c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
         "ragarc_merge_topk_inbox": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_double, P, P]),
+        "ragarc_l2_aug_dim": (c_int, [c_int, c_int]),
+        "ragarc_l2_augment": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+        "ragarc_l2_distances": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         "ragarc_normalize_split3": (c_int, [P, P, c_int64, c_int, c_int, P]),
         "ragarc_dense_topk_x3_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
         "ragarc_dense_topk_x3": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, c_size_t, P]),

@@ -53,7 +53,23 @@ class PooledEncoderEmbeddingsConfig(AbstractConfig):
         return EmbeddingsModule(config=self)
 
 
-EmbeddingsConfig = Annotated[Union[HashEmbeddingsConfig, PooledEncoderEmbeddingsConfig], Field(discriminator="type")]
+class HuggingFaceEmbeddingsConfig(AbstractConfig):
+    """The reference's ``HuggingFaceEmbeddings`` fields (core/file_management/embeddings/huggingface.py:67-83)
+    as a registry config: builds the same-named class of this package."""
+    type: Literal["huggingface_embeddings"] = "huggingface_embeddings"
+    model_name: str = "sentence-transformers/all-mpnet-base-v2"
+    cache_folder: Optional[str] = None
+    model_kwargs: dict = Field(default_factory=dict)
+    encode_kwargs: dict = Field(default_factory=dict)
+    multi_process: bool = False
+    show_progress_bar: bool = False
+
+    def build(self):
+        return EmbeddingsModule(config=self)
+
+
+EmbeddingsConfig = Annotated[Union[HashEmbeddingsConfig, PooledEncoderEmbeddingsConfig, HuggingFaceEmbeddingsConfig],
+                             Field(discriminator="type")]
 
 
 @dataclass
@@ -65,6 +81,11 @@ class EmbeddingsModule(AbstractModule):
         c = self.config
         if c.type == "hash_embeddings":
             self.impl = HashEmbeddings(dim=c.dim, seed=c.seed)
+        elif c.type == "huggingface_embeddings":
+            from .core.file_management.embeddings.huggingface import HuggingFaceEmbeddings
+            self.impl = HuggingFaceEmbeddings(model_name=c.model_name, cache_folder=c.cache_folder,
+                                              model_kwargs=c.model_kwargs, encode_kwargs=c.encode_kwargs,
+                                              multi_process=c.multi_process, show_progress_bar=c.show_progress_bar)
         else:
             self.impl = B200PooledEmbeddings.from_pretrained(
                 c.model_name, pooling=c.pooling, normalize_embeddings=c.normalize_embeddings, device=c.device,
@@ -82,7 +103,7 @@ class B200VectorStoreConfig(AbstractConfig):
     type: Literal["b200_vector_store"] = "b200_vector_store"
     embedding: EmbeddingsConfig
     metric: Literal["cosine", "ip"] = "cosine"
-    dtype: Literal["float32", "bfloat16", "float16"] = "float32"
+    dtype: Literal["float32", "float32x3", "float32_exact", "bfloat16", "float16"] = "float32"
     device: str = "cuda"
     corpus_path: Optional[str] = None       # JSON(L) corpus to index at build time
     index_path: Optional[str] = None        # folder written by save_local

@@ -12,7 +12,8 @@
 
 struct ragarc_index {
   int d = 0, dtype = RAGARC_F32, metric = RAGARC_METRIC_IP, device = 0;
-  void* rows = nullptr;           // [cap, d] storage dtype
+  int ds = 0;                     // stored row width: d, or ragarc_l2_aug_dim(d, dtype) for RAGARC_METRIC_L2
+  void* rows = nullptr;           // [cap, ds] storage dtype
   int64_t n = 0, cap = 0;
   void* ws = nullptr;             // dense_topk workspace
   size_t ws_bytes = 0;
@@ -69,7 +70,7 @@ static int reserve_rows(ragarc_index* ix, int64_t capacity, cudaStream_t st) {
   while (cap < capacity) cap += cap / 2 + 1024;          // geometric growth: O(1) amortised copies
   if (capacity > ix->cap * 4) cap = capacity;            // bulk load: exact size, no slack
   void* fresh = nullptr;
-  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  const size_t row_bytes = (size_t)ix->ds * esize(ix->dtype);
   RA_CUDA(cudaMalloc(&fresh, (size_t)cap * row_bytes));
   if (ix->n > 0) RA_CUDA(cudaMemcpyAsync(fresh, ix->rows, (size_t)ix->n * row_bytes, cudaMemcpyDeviceToDevice, st));
   RA_CUDA(cudaDeviceSynchronize());
@@ -115,12 +116,14 @@ int ragarc_index_create(int d, int dtype, int metric, ragarc_index_t** out) {
   *out = nullptr;
   RA_REQUIRE(d > 0, "index_create: d=%d", d);
   RA_REQUIRE(dtype == RAGARC_F32 || dtype == RAGARC_BF16 || dtype == RAGARC_F16, "index_create: bad dtype %d", dtype);
-  RA_REQUIRE(metric == RAGARC_METRIC_IP || metric == RAGARC_METRIC_COSINE, "index_create: bad metric %d", metric);
+  RA_REQUIRE(metric == RAGARC_METRIC_IP || metric == RAGARC_METRIC_COSINE || metric == RAGARC_METRIC_L2,
+             "index_create: bad metric %d", metric);
   int dev = 0;
   RA_CUDA(cudaGetDevice(&dev));
   ragarc_index* ix = new (std::nothrow) ragarc_index();
   RA_REQUIRE(ix != nullptr, "index_create: out of host memory");
   ix->d = d; ix->dtype = dtype; ix->metric = metric; ix->device = dev;
+  ix->ds = metric == RAGARC_METRIC_L2 ? ragarc_l2_aug_dim(d, dtype) : d;
   if (cudaEventCreateWithFlags(&ix->last, cudaEventDisableTiming) != cudaSuccess) {
     delete ix;
     set_error("index_create: cannot create a CUDA event: %s", cudaGetErrorString(cudaGetLastError()));
@@ -170,10 +173,13 @@ int ragarc_index_add(ragarc_index_t* ix, const float* rows, int64_t n, int rows_
   if (rc) return rc;
   rc = reserve_rows(ix, ix->n + n, st);
   if (rc) return rc;
-  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  const size_t row_bytes = (size_t)ix->ds * esize(ix->dtype);
   const int normalize = ix->metric == RAGARC_METRIC_COSINE;
+  const bool l2 = ix->metric == RAGARC_METRIC_L2;
   if (!rows_on_host) {
-    rc = ragarc_normalize_cast(rows, (char*)ix->rows + (size_t)ix->n * row_bytes, n, ix->d, ix->dtype, normalize, stream);
+    void* dst = (char*)ix->rows + (size_t)ix->n * row_bytes;
+    rc = l2 ? ragarc_l2_augment(rows, dst, n, ix->d, ix->dtype, 0, 0, nullptr, stream)
+            : ragarc_normalize_cast(rows, dst, n, ix->d, ix->dtype, normalize, stream);
     if (rc) return rc;
   } else {
     // host rows travel through a bounded device staging buffer (<= 256 MB of fp32 at a time)
@@ -185,8 +191,9 @@ int ragarc_index_add(ragarc_index_t* ix, const float* rows, int64_t n, int rows_
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
       const int64_t c = n - r0 < chunk ? n - r0 : chunk;
       RA_CUDA(cudaMemcpyAsync(ix->stage, rows + (size_t)r0 * ix->d, (size_t)c * ix->d * 4, cudaMemcpyHostToDevice, st));
-      rc = ragarc_normalize_cast((const float*)ix->stage, (char*)ix->rows + (size_t)(ix->n + r0) * row_bytes, c, ix->d,
-                                 ix->dtype, normalize, stream);
+      void* dst = (char*)ix->rows + (size_t)(ix->n + r0) * row_bytes;
+      rc = l2 ? ragarc_l2_augment((const float*)ix->stage, dst, c, ix->d, ix->dtype, 0, 0, nullptr, stream)
+              : ragarc_normalize_cast((const float*)ix->stage, dst, c, ix->d, ix->dtype, normalize, stream);
       if (rc) return rc;
     }
     RA_CUDA(cudaStreamSynchronize(st));        // the caller may reuse its host buffer on return
@@ -206,14 +213,14 @@ int ragarc_index_search(ragarc_index_t* ix, const float* queries, int nq, int k,
   RA_REQUIRE(g.ok, "index_search: cannot select device %d", ix->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t q32_bytes = align_up((size_t)nq * ix->d * 4, 256);
-  const size_t qs_bytes = align_up((size_t)nq * ix->d * esize(ix->dtype), 256);
+  const size_t qs_bytes = align_up((size_t)nq * ix->ds * esize(ix->dtype), 256);
   const size_t os_bytes = align_up((size_t)nq * k * 4, 256);
   const size_t oi_bytes = align_up((size_t)nq * k * 8, 256);
   int rc = order_begin(ix, st);
   if (rc) return rc;
   rc = grow_buffer(&ix->stage, &ix->stage_bytes, q32_bytes + qs_bytes + os_bytes + oi_bytes, st);
   if (rc) return rc;
-  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->d, ix->dtype, nq, k);
+  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->ds, ix->dtype, nq, k);
   RA_REQUIRE(need_ws > 0, "index_search: unsupported shape (k=%d)", k);
   rc = grow_buffer(&ix->ws, &ix->ws_bytes, need_ws, st);
   if (rc) return rc;
@@ -230,14 +237,23 @@ int ragarc_index_search(ragarc_index_t* ix, const float* queries, int nq, int k,
   // faiss.normalize_L2 on the query when the metric is cosine (VectorStore_Faiss.py:259), then the
   // cast to the storage dtype; for fp32 storage without normalisation the queries are used in place
   const void* q_use = q_src;
-  if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
+  const bool l2 = ix->metric == RAGARC_METRIC_L2;
+  if (l2) {
+    rc = ragarc_l2_augment(q_src, qs, nq, ix->d, ix->dtype, 1, 0, nullptr, stream);     // [q | 1]
+    if (rc) return rc;
+    q_use = qs;
+  } else if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
     rc = ragarc_normalize_cast(q_src, qs, nq, ix->d, ix->dtype, ix->metric == RAGARC_METRIC_COSINE, stream);
     if (rc) return rc;
     q_use = qs;
   }
-  rc = ragarc_dense_topk(ix->rows, ix->n, ix->d, ix->dtype, q_use, nq, k, d_scores, d_ids, ix->ws, ix->ws_bytes,
+  rc = ragarc_dense_topk(ix->rows, ix->n, ix->ds, ix->dtype, q_use, nq, k, d_scores, d_ids, ix->ws, ix->ws_bytes,
                          RAGARC_DENSE_AUTO, nullptr, stream);
   if (rc) return rc;
+  if (l2) {                                                                              // kept values -> squared distances
+    rc = ragarc_l2_distances(d_scores, qs, ix->dtype, nq, k, ix->d, stream);
+    if (rc) return rc;
+  }
   if (buffers_on_host) {
     RA_CUDA(cudaMemcpyAsync(out_scores, d_scores, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     RA_CUDA(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -269,7 +285,7 @@ int ragarc_index_remove(ragarc_index_t* ix, const int64_t* rows_host, int64_t n_
   map.reserve((size_t)ix->n);
   for (int64_t r = 0; r < ix->n; ++r) if (!drop[(size_t)r]) map.push_back(r);
   const int64_t n_out = (int64_t)map.size();
-  const size_t row_bytes = (size_t)ix->d * esize(ix->dtype);
+  const size_t row_bytes = (size_t)ix->ds * esize(ix->dtype);
   void* fresh = nullptr;
   int64_t* d_map = nullptr;
   const int64_t cap = n_out > 0 ? n_out : 1;
@@ -336,6 +352,8 @@ int ragarc_sharded_create(int d, int dtype, int metric, int n_shards, const int*
   RA_REQUIRE(out != nullptr, "sharded_create: out is NULL");
   *out = nullptr;
   RA_REQUIRE(n_shards >= 1 && n_shards <= 64, "sharded_create: n_shards=%d", n_shards);
+  RA_REQUIRE(metric == RAGARC_METRIC_IP || metric == RAGARC_METRIC_COSINE,
+             "sharded_create: metric %d is not offered sharded (inner product / cosine only)", metric);
   int ndev = 0;
   RA_CUDA(cudaGetDeviceCount(&ndev));
   ragarc_sharded_index* sh = new (std::nothrow) ragarc_sharded_index();

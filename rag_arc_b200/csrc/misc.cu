@@ -45,6 +45,71 @@ __global__ void normalize_cast_kernel(const float* __restrict__ src, T* __restri
   for (int i = lane; i < d; i += 32) o[i] = from_f32<T>(__fmul_rn(s[i], scale));
 }
 
+// ---- squared-L2 search through the inner-product kernels -----------------------------------------
+// ||q - x||^2 = ||q||^2 - 2 (q.x - ||x||^2 / 2): a row is stored as [x | h] with h = -||x||^2/2 and a
+// query as [q | 1], so that the UNCHANGED scoring + selection kernels rank by q.x + h (largest first
+// = nearest first) and a tiny epilogue turns the k kept values into distances.  For half-precision
+// storage h is carried as three pieces h1 + h2 + h3 (each the rounding of what is left, as in
+// normalize_split3) against three ones in the query, so it reaches the fp32 accumulator with ~2^-24
+// relative error instead of the storage type's 2^-8 / 2^-11; ||x||^2 is taken over the STORED
+// (rounded) values, i.e. distances are exact for what the index holds.  One warp per row.
+template <typename T>
+__global__ void l2_augment_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n, int d, int d_aug,
+                                  int is_query, int normalize, float* __restrict__ sqnorm) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = src + (size_t)row * d;
+  T* o = dst + (size_t)row * d_aug;
+  float scale = 1.0f;
+  if (normalize) {
+    float nr = 0.f;
+    for (int i = lane; i < d; i += 32) { float v = s[i]; nr = fmaf(v, v, nr); }
+    nr = warp_sum(nr);
+    if (nr > 0.f) scale = __fdiv_rn(1.0f, __fsqrt_rn(nr));
+  }
+  float xn = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const T t = from_f32<T>(__fmul_rn(s[i], scale));
+    o[i] = t;
+    const float v = load_f32(&t);
+    xn = fmaf(v, v, xn);
+  }
+  xn = warp_sum(xn);
+  if (lane == 0) {
+    if (sqnorm) sqnorm[row] = xn;
+    const float h = -0.5f * xn;
+    if (sizeof(T) == 4) {
+      o[d] = from_f32<T>(is_query ? 1.0f : h);
+    } else {
+      const T h1 = from_f32<T>(h);
+      const float r1 = h - load_f32(&h1);
+      const T h2 = from_f32<T>(r1);
+      const float r2 = r1 - load_f32(&h2);
+      const T one = from_f32<T>(1.0f), zero = from_f32<T>(0.0f);
+      o[d] = is_query ? one : h1; o[d + 1] = is_query ? one : h2; o[d + 2] = is_query ? one : from_f32<T>(r2);
+      for (int i = d + 3; i < d_aug; ++i) o[i] = zero;
+    }
+  }
+}
+
+// scores[q][j] (= q.x - ||x||^2/2 of the j-th best row, descending) -> squared distances (ascending);
+// ||q||^2 is recomputed from the stored query values.  FAISS clamps its BLAS path at 0 as well.
+template <typename T>
+__global__ void l2_finish_kernel(float* __restrict__ scores, const T* __restrict__ q_aug, int nq, int k, int d, int d_aug) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const int lane = threadIdx.x & 31;
+  const T* s = q_aug + (size_t)q * d_aug;
+  float qn = 0.f;
+  for (int i = lane; i < d; i += 32) { const float v = load_f32(s + i); qn = fmaf(v, v, qn); }
+  qn = warp_sum(qn);
+  for (int j = lane; j < k; j += 32) {
+    const float sc = scores[(size_t)q * k + j];
+    scores[(size_t)q * k + j] = sc == -INFINITY ? INFINITY : fmaxf(0.0f, fmaf(-2.0f, sc, qn));
+  }
+}
+
 // ---- normalize + split into three bf16 planes: v = b1 + b2 + b3 up to 2^-24 relative ------------
 __global__ void normalize_split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
                                         int d, int normalize) {
@@ -368,6 +433,44 @@ int ragarc_normalize_split3(const float* src, void* dst, int64_t n, int d, int n
   const int warps = 8;
   normalize_split3_kernel<<<(unsigned)ceil_div(n, warps), warps * 32, 0, (cudaStream_t)stream>>>(
       src, (__nv_bfloat16*)dst, n, d, normalize);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_l2_aug_dim(int d, int dtype) {
+  if (d <= 0) return 0;
+  return dtype == RAGARC_F32 ? d + 1 : (d + 3 + 7) / 8 * 8;
+}
+
+int ragarc_l2_augment(const float* src, void* dst, int64_t n, int d, int dst_dtype, int is_query, int normalize,
+                      float* sqnorm_out, void* stream) {
+  RA_REQUIRE(n >= 0 && d > 0, "l2_augment: bad shape n=%lld d=%d", (long long)n, d);
+  RA_REQUIRE(dst_dtype == RAGARC_F32 || dst_dtype == RAGARC_BF16 || dst_dtype == RAGARC_F16, "l2_augment: bad dtype %d", dst_dtype);
+  if (n == 0) return RAGARC_OK;
+  RA_REQUIRE(src && dst, "l2_augment: null pointer");
+  const int d_aug = ragarc_l2_aug_dim(d, dst_dtype);
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(n, warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == RAGARC_F32) l2_augment_kernel<float><<<grid, warps * 32, 0, st>>>(src, (float*)dst, n, d, d_aug, is_query, normalize, sqnorm_out);
+  else if (dst_dtype == RAGARC_BF16) l2_augment_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>(src, (__nv_bfloat16*)dst, n, d, d_aug, is_query, normalize, sqnorm_out);
+  else l2_augment_kernel<__half><<<grid, warps * 32, 0, st>>>(src, (__half*)dst, n, d, d_aug, is_query, normalize, sqnorm_out);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_l2_distances(float* scores, const void* queries_aug, int dtype, int nq, int k, int d, void* stream) {
+  RA_REQUIRE(nq >= 0 && k > 0 && d > 0, "l2_distances: bad shape nq=%d k=%d d=%d", nq, k, d);
+  RA_REQUIRE(dtype == RAGARC_F32 || dtype == RAGARC_BF16 || dtype == RAGARC_F16, "l2_distances: bad dtype %d", dtype);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(scores && queries_aug, "l2_distances: null pointer");
+  const int d_aug = ragarc_l2_aug_dim(d, dtype);
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(nq, warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RAGARC_F32) l2_finish_kernel<float><<<grid, warps * 32, 0, st>>>(scores, (const float*)queries_aug, nq, k, d, d_aug);
+  else if (dtype == RAGARC_BF16) l2_finish_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>(scores, (const __nv_bfloat16*)queries_aug, nq, k, d, d_aug);
+  else l2_finish_kernel<__half><<<grid, warps * 32, 0, st>>>(scores, (const __half*)queries_aug, nq, k, d, d_aug);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

@@ -17,8 +17,8 @@ reference class (:68-513).  What changes underneath:
 * batched entry points (``search_batch``, ``similarity_search_batch``) sit next to the
   single-query methods - the reference has none.
 
-Only exact ("flat") search is offered; ``index_type`` "ivf"/"hnsw" (approximate in the
-reference) and metric "l2" raise ``ValueError``.
+Only exact ("flat") search is offered - all three metrics of the reference (cosine, ip, l2);
+``index_type`` "ivf"/"hnsw" (approximate in the reference) raise ``ValueError``.
 """
 from __future__ import annotations
 
@@ -42,8 +42,12 @@ def _is_x3(dt) -> bool:
     return isinstance(dt, str) and dt.lower() in ("float32x3", "fp32x3", "bf16x3")
 
 
+def _is_exact_fp32(dt) -> bool:
+    return isinstance(dt, str) and dt.lower() in ("float32_exact", "fp32_exact")
+
+
 def _as_dtype(dt) -> torch.dtype:
-    if _is_x3(dt):
+    if _is_x3(dt) or _is_exact_fp32(dt):
         return torch.float32
     if isinstance(dt, torch.dtype):
         if dt not in ops._DT:
@@ -59,7 +63,7 @@ class FlatIndexB200:
     """The slice of the ``faiss.IndexFlatIP`` API the reference uses (``d``, ``ntotal``,
     ``is_trained``, ``add``, ``reset``, ``search``) over a device-resident matrix."""
 
-    def __init__(self, d: int, dtype: torch.dtype, device, normalize: bool, x3: bool = False):
+    def __init__(self, d: int, dtype: torch.dtype, device, normalize: bool, x3: bool = False, l2: bool = False):
         self.d = int(d)
         self.dtype = dtype
         self.device = torch.device(device)
@@ -67,6 +71,11 @@ class FlatIndexB200:
         self.is_trained = True
         self.ntotal = 0
         self.rows = torch.empty((0, self.d), dtype=dtype, device=self.device)
+        # metric "l2" (faiss.IndexFlatL2): next to the plain rows, the augmented matrix [x | -|x|^2/2]
+        # the inner-product kernels search (ragarc_l2_augment); results are squared distances, ascending
+        self.l2 = bool(l2)
+        self.d_aug = ops.l2_aug_dim(self.d, dtype) if l2 else self.d
+        self.aug = torch.empty((0, self.d_aug), dtype=dtype, device=self.device) if l2 else None
         # "float32x3": fp32 master rows + three bf16 planes per row for fp32-accurate tensor-core search
         self.x3 = bool(x3)
         self.planes = torch.empty((0, 3 * self.d), dtype=torch.bfloat16, device=self.device) if x3 else None
@@ -85,6 +94,11 @@ class FlatIndexB200:
             if self.ntotal:
                 gp[:self.ntotal].copy_(self.planes[:self.ntotal])
             self.planes = gp
+        if self.l2:
+            ga = torch.empty((new_cap, self.d_aug), dtype=self.dtype, device=self.device)
+            if self.ntotal:
+                ga[:self.ntotal].copy_(self.aug[:self.ntotal])
+            self.aug = ga
 
     def add(self, x) -> None:
         """x: fp32 [n,d] numpy array or tensor (host or device); normalised (if the store's metric
@@ -98,6 +112,8 @@ class FlatIndexB200:
         ops.normalize_cast(xt, self.dtype, self.normalize, out=self.rows[self.ntotal:self.ntotal + n])
         if self.x3:
             ops.normalize_split3(xt, self.normalize, out=self.planes[self.ntotal:self.ntotal + n])
+        if self.l2:
+            ops.l2_augment(xt, self.dtype, is_query=False, normalize=self.normalize, out=self.aug[self.ntotal:self.ntotal + n])
         self.ntotal += n
 
     def add_prepared(self, rows: torch.Tensor) -> None:
@@ -108,6 +124,9 @@ class FlatIndexB200:
         if self.x3:
             ops.normalize_split3(rows.to(torch.float32).contiguous(), False,
                                  out=self.planes[self.ntotal:self.ntotal + n])
+        if self.l2:
+            ops.l2_augment(rows.to(torch.float32).contiguous(), self.dtype, is_query=False, normalize=False,
+                           out=self.aug[self.ntotal:self.ntotal + n])
         self.ntotal += n
 
     def reset(self) -> None:
@@ -120,11 +139,25 @@ class FlatIndexB200:
         qt = qt.to(device=self.device, dtype=torch.float32).contiguous()
         if self.x3:
             return ops.normalize_split3(qt, self.normalize)
+        if self.l2:
+            return ops.l2_augment(qt, self.dtype, is_query=True, normalize=self.normalize)      # [q | 1]
         return ops.normalize_cast(qt, self.dtype, self.normalize)
+
+    def prepare_plain(self, q) -> torch.Tensor:
+        """Queries in the row space of ``rows`` (normalised if the store normalises, storage dtype),
+        e.g. for MMR, whatever form ``prepare_queries`` needs for searching."""
+        qt = torch.as_tensor(q)
+        if qt.dim() == 1:
+            qt = qt[None, :]
+        qt = qt.to(device=self.device, dtype=torch.float32).contiguous()
+        return ops.normalize_cast(qt, torch.float32 if self.x3 else self.dtype, self.normalize)
 
     def search_device(self, q_prepared: torch.Tensor, k: int):
         if self.x3:
             return ops.dense_topk_x3(self.planes, q_prepared, k, n_rows=self.ntotal)
+        if self.l2:
+            scores, rows = ops.dense_topk(self.aug, q_prepared, k, n_rows=self.ntotal)
+            return ops.l2_distances(scores, q_prepared, self.d), rows                            # squared L2, ascending
         return ops.dense_topk(self.rows, q_prepared, k, n_rows=self.ntotal)
 
     def capture_search(self, queries: torch.Tensor, k: int):
@@ -187,7 +220,7 @@ class SearchPipeline:
             self._capture()
 
     def _index_state(self):
-        rows = self.index.planes if self.index.x3 else self.index.rows
+        rows = self.index.planes if self.index.x3 else (self.index.aug if self.index.l2 else self.index.rows)
         return (rows.data_ptr(), self.index.ntotal)
 
     def _capture(self) -> None:
@@ -278,6 +311,12 @@ class B200VectorStore(VectorStore):
         self.index = index
         self.dtype = _as_dtype(dtype)
         self.x3 = _is_x3(dtype)
+        # dtype="float32" (the default, the reference's precision): fp32 master rows, searched on the
+        # tensor cores through three bf16 planes whenever the dimension allows (d % 64 == 0, scores within
+        # 2e-6 of the fp32 FMA result at 8x its speed); "float32_exact" pins the CUDA-core fp32 FMA path
+        self.auto_x3 = (not self.x3) and (not _is_exact_fp32(dtype)) and self.dtype == torch.float32
+        self.dtype_name = ("float32x3" if self.x3 else "float32_exact" if _is_exact_fp32(dtype)
+                           else str(self.dtype).replace("torch.", ""))
         self.device = torch.device(device)
         self.docstore: dict[str, Document] = {}
         self.index_to_docstore_id: dict[int, str] = {}
@@ -294,11 +333,13 @@ class B200VectorStore(VectorStore):
             raise ValueError(f"unsupported metric: {self.metric}")
         if self.index_type != "flat":
             raise ValueError(f"unsupported index type: {self.index_type} (B200VectorStore is exact/flat only)")
-        if self.metric == "l2":
-            raise ValueError("metric 'l2' is not offered by B200VectorStore (inner product / cosine only)")
+        if self.metric == "l2" and self.x3:
+            raise ValueError("dtype 'float32x3' is offered for the inner-product / cosine metrics only")
         if self.x3 and dimension % 64 != 0:
             raise ValueError("dtype 'float32x3' needs an embedding dimension that is a multiple of 64")
-        return FlatIndexB200(dimension, self.dtype, self.device, self._normalizes(), x3=self.x3)
+        x3 = self.x3 or (self.auto_x3 and dimension % 64 == 0 and self.metric != "l2")
+        return FlatIndexB200(dimension, self.dtype, self.device, self._normalizes(), x3=x3,
+                             l2=self.metric == "l2")
 
     def _normalizes(self) -> bool:
         return bool(self.normalize_L2 or self.metric == "cosine")
@@ -439,9 +480,8 @@ class B200VectorStore(VectorStore):
         _, cand = self.index.search_device(q, fetch)
         if k >= fetch:
             return self.rows_to_documents(cand[0].tolist())
-        if self.index.x3:      # MMR works on the fp32 master rows
-            q = ops.normalize_cast(torch.as_tensor(np.asarray([embedding], dtype=np.float32)).to(self.device),
-                                   torch.float32, self.index.normalize)
+        if self.index.x3 or self.index.l2:      # MMR works on the plain (fp32 master / un-augmented) rows
+            q = self.index.prepare_plain(np.asarray([embedding], dtype=np.float32))
         sel = ops.mmr_select(self.index.rows, q, cand.contiguous(), k, lambda_mult, n_rows=self.ntotal)
         cand_h = cand[0].tolist()
         return self.rows_to_documents([cand_h[j] for j in sel[0].tolist() if j >= 0])
@@ -499,7 +539,7 @@ class B200VectorStore(VectorStore):
             np.save(os.path.join(folder_path, f"{index_name}.b200.npy"), host)
         side = {"docstore": self.docstore, "index_to_docstore_id": self.index_to_docstore_id,
                 "index_type": self.index_type, "metric": self.metric, "normalize_L2": self.normalize_L2,
-                "dtype": "float32x3" if self.x3 else str(self.dtype).replace("torch.", "")}
+                "dtype": self.dtype_name}
         with open(os.path.join(folder_path, f"{index_name}.pkl"), "wb") as fh:
             pickle.dump(side, fh)
 

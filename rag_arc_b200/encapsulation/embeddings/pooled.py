@@ -54,18 +54,22 @@ class B200PooledEmbeddings(Embeddings):
 
     @classmethod
     def from_pretrained(cls, model_name: str, pooling: str = "mean", normalize_embeddings: bool = True,
-                        device="cuda", dtype=torch.float16, max_length: int = 512, **kwargs):
+                        device="cuda", dtype=torch.float16, max_length: int = 512, cache_dir=None,
+                        trust_remote_code: bool = False, local_files_only: bool = False, **kwargs):
         """Wrap a HuggingFace ``AutoModel`` (weights must be available locally)."""
         from transformers import AutoModel, AutoTokenizer
-        tok = AutoTokenizer.from_pretrained(model_name)
-        model = AutoModel.from_pretrained(model_name, torch_dtype=dtype).to(device).eval()
+        hub = dict(cache_dir=cache_dir, trust_remote_code=trust_remote_code, local_files_only=local_files_only)
+        tok = AutoTokenizer.from_pretrained(model_name, **hub)
+        model = AutoModel.from_pretrained(model_name, dtype=dtype, **hub).to(device).eval()
 
         @torch.no_grad()
         def encoder(texts):
             enc = tok(texts, padding=True, truncation=True, max_length=max_length, return_tensors="pt").to(device)
             return model(**enc).last_hidden_state, enc["attention_mask"]
 
-        return cls(encoder, pooling=pooling, normalize_embeddings=normalize_embeddings, **kwargs)
+        self = cls(encoder, pooling=pooling, normalize_embeddings=normalize_embeddings, **kwargs)
+        self.tokenizer, self.model = tok, model
+        return self
 
 
 class TableEmbeddings(Embeddings):

@@ -15,7 +15,7 @@ import numpy as np
 from . import _native as N
 
 _DTYPES = {"float32": N.F32, "bfloat16": N.BF16, "float16": N.F16}
-_METRICS = {"ip": N.METRIC_IP, "cosine": N.METRIC_COSINE}
+_METRICS = {"ip": N.METRIC_IP, "cosine": N.METRIC_COSINE, "l2": N.METRIC_L2}
 
 
 class NativeFlatIndex:
@@ -23,7 +23,7 @@ class NativeFlatIndex:
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
         if metric not in _METRICS:
-            raise ValueError(f"metric must be one of {sorted(_METRICS)} (exact inner product / cosine only)")
+            raise ValueError(f"metric must be one of {sorted(_METRICS)}")
         self.d, self.dtype, self.metric = int(d), dtype, metric
         h = ctypes.c_void_p()
         N.check(N.lib.ragarc_index_create(self.d, _DTYPES[dtype], _METRICS[metric], ctypes.byref(h)), "index_create")
@@ -46,7 +46,8 @@ class NativeFlatIndex:
 
     def search(self, q: np.ndarray, k: int):
         """q: float32 [nq, d] host array -> (D float32 [nq,k] descending, I int64 [nq,k], -1 padded):
-        the return contract of ``faiss.IndexFlatIP.search``."""
+        the return contract of ``faiss.IndexFlatIP.search`` (metric "l2": squared distances ascending,
+        that of ``faiss.IndexFlatL2.search``)."""
         q = np.ascontiguousarray(q, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.d:
             raise ValueError(f"expected [nq,{self.d}] float32 queries")
@@ -84,7 +85,7 @@ class NativeShardedIndex:
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
         if metric not in _METRICS:
-            raise ValueError(f"metric must be one of {sorted(_METRICS)} (exact inner product / cosine only)")
+            raise ValueError(f"metric must be one of {sorted(_METRICS)}")
         self.d, self.dtype, self.metric, self.devices = int(d), dtype, metric, tuple(int(x) for x in devices)
         devs = (ctypes.c_int * len(self.devices))(*self.devices)
         h = ctypes.c_void_p()

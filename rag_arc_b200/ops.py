@@ -104,6 +104,38 @@ def normalize_cast(src: torch.Tensor, dtype: torch.dtype = torch.float32, normal
     return out
 
 
+def l2_aug_dim(d: int, dtype: torch.dtype) -> int:
+    return int(N.lib.ragarc_l2_aug_dim(int(d), dtype_code(dtype)))
+
+
+def l2_augment(src: torch.Tensor, dtype: torch.dtype, *, is_query: bool, normalize: bool = False,
+               out: Optional[torch.Tensor] = None, sqnorm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [n,d] -> [n, l2_aug_dim(d)] of ``dtype``: rows as [x | -|x|^2/2], queries as [q | 1]
+    (squared-L2 search on the inner-product kernels, see ragarc_b200.h)."""
+    _cuda(src, "src")
+    if src.dtype != torch.float32 or src.dim() != 2:
+        raise N.RagArcError("l2_augment expects a 2-D float32 tensor")
+    n, d = src.shape
+    da = l2_aug_dim(d, dtype)
+    if out is None:
+        out = torch.empty((n, da), dtype=dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        N.check(N.lib.ragarc_l2_augment(src.data_ptr(), out.data_ptr(), n, d, dtype_code(dtype), int(bool(is_query)),
+                                        int(bool(normalize)), sqnorm.data_ptr() if sqnorm is not None else None,
+                                        _stream_ptr(src.device)), "l2_augment")
+    return out
+
+
+def l2_distances(scores: torch.Tensor, queries_aug: torch.Tensor, d: int) -> torch.Tensor:
+    """In place: the kept values of a search over augmented matrices -> squared L2 distances."""
+    _cuda(scores, "scores"); _cuda(queries_aug, "queries_aug")
+    nq, k = scores.shape
+    with torch.cuda.device(scores.device):
+        N.check(N.lib.ragarc_l2_distances(scores.data_ptr(), queries_aug.data_ptr(), dtype_code(queries_aug.dtype), nq, k,
+                                          int(d), _stream_ptr(scores.device)), "l2_distances")
+    return scores
+
+
 def dense_workspace_bytes(n: int, d: int, dtype: torch.dtype, nq: int, k: int) -> int:
     return int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, dtype_code(dtype), nq, k))
 

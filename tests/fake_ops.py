@@ -91,12 +91,50 @@ def _pool_normalize(x, mask, mode="mean", normalize=True):
     return torch.from_numpy(opool.pool_normalize(x.float().numpy(), mask.numpy(), mode, normalize).astype(np.float32))
 
 
+def _l2_aug_dim(d, dtype):
+    return d + 1 if dtype == torch.float32 else (d + 3 + 7) // 8 * 8
+
+
+def _l2_augment(src, dtype, *, is_query, normalize=False, out=None, sqnorm=None):
+    """[x | -|x|^2/2] / [q | 1] with the extra term split into three storage-dtype pieces for half
+    types - the layout of ragarc_l2_augment, restated with torch on the host."""
+    x = _normalize_cast(src, dtype, normalize)
+    n, d = x.shape
+    da = _l2_aug_dim(d, dtype)
+    res = torch.zeros((n, da), dtype=dtype)
+    res[:, :d] = x
+    xn = (x.float() * x.float()).sum(1, dtype=torch.float32)
+    if is_query:
+        res[:, d:d + (1 if dtype == torch.float32 else 3)] = 1
+    elif dtype == torch.float32:
+        res[:, d] = -0.5 * xn
+    else:
+        h = -0.5 * xn
+        h1 = h.to(dtype); r1 = h - h1.float(); h2 = r1.to(dtype); r2 = r1 - h2.float()
+        res[:, d], res[:, d + 1], res[:, d + 2] = h1, h2, r2.to(dtype)
+    if sqnorm is not None:
+        sqnorm.copy_(xn)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def _l2_distances(scores, queries_aug, d):
+    qn = (queries_aug[:, :d].float() ** 2).sum(1, dtype=torch.float32)
+    dist = torch.clamp(qn[:, None] - 2.0 * scores, min=0.0)
+    dist[torch.isinf(scores)] = float("inf")
+    scores.copy_(dist)
+    return scores
+
+
 @contextlib.contextmanager
 def patched():
     from rag_arc_b200 import ops
     fakes = {"normalize_cast": _normalize_cast, "dense_topk": _dense_topk, "mmr_select": _mmr_select,
              "bm25_scores": _bm25_scores, "bm25_topk": _bm25_topk, "rrf_fuse": _rrf_fuse,
-             "pool_normalize": _pool_normalize}
+             "pool_normalize": _pool_normalize, "l2_aug_dim": _l2_aug_dim, "l2_augment": _l2_augment,
+             "l2_distances": _l2_distances}
     saved = {name: getattr(ops, name) for name in fakes}
     try:
         for name, fn in fakes.items():

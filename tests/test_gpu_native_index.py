@@ -108,3 +108,32 @@ def test_single_process_sharded_index_equals_flat_index(dev, dtype, metric):
     assert np.array_equal(I, Is) and np.array_equal(D, Ds)
     for o in (flat, sh, tiny, ft):
         o.close()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
+def test_l2_index_matches_indexflatl2_restatement(dev, dtype):
+    """ragarc_index_* with RAGARC_METRIC_L2 against oracle.dense.IndexFlatL2 (squared distances
+    ascending) on the values the index stores (storage-dtype rounding applied to both sides), incl.
+    un-normalised rows of very different norms, remove, and k > ntotal padding."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, d, nq, k = 20_000, 100, 37, 10                       # d % 8 != 0 for fp32 (SIMT), augmented width pads for half types
+    X = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, size=(n, 1))).astype(np.float32)
+    Q = (X[rng.integers(0, n, nq)] + 0.1 * rng.standard_normal((nq, d))).astype(np.float32)
+    tdt = {"float32": torch.float32, "bfloat16": torch.bfloat16, "float16": torch.float16}[dtype]
+    Xr = torch.from_numpy(X).to(tdt).float().numpy(); Qr = torch.from_numpy(Q).to(tdt).float().numpy()
+    ref = odense.IndexFlatL2(d); ref.add(Xr)
+    idx = NativeFlatIndex(d, dtype, "l2"); idx.add(X)
+    D, I = idx.search(Q, k)
+    Dr, Ir = ref.search(Qr, k)
+    assert (np.diff(D, axis=1) >= 0).all()
+    assert np.allclose(D, Dr, rtol=1e-5, atol=1e-4 * max(1.0, float(Dr.max())))
+    assert (I == Ir).mean() > 0.99
+    true = ((Qr[:, None, :].astype(np.float64) - Xr[I].astype(np.float64)) ** 2).sum(-1)
+    assert np.allclose(D, true, rtol=1e-4, atol=1e-3)      # the returned rows really are at that distance
+    idx.remove(I[:, 0].tolist())
+    D2, I2 = idx.search(Q[:3], 3)
+    assert (D2[:, 0] >= D[:3, 0] - 1e-6).all() and idx.ntotal == n - len(set(I[:, 0].tolist()))
+    small = NativeFlatIndex(d, dtype, "l2"); small.add(X[:4])
+    D3, I3 = small.search(Q[:2], 6)
+    assert (I3[:, 4:] == -1).all() and np.isinf(D3[:, 4:]).all() and sorted(I3[0, :4].tolist()) == [0, 1, 2, 3]

@@ -1,0 +1,201 @@
+"""GPU parity at the full BASELINE shapes, every query against every row (not a sample), plus the
+direct kernel-level checks the plugin tests only reach indirectly.
+
+* C3  1M x 768 bf16, 1024 queries, top-100: all ids / scores against a chunked fp32 matmul + topk that
+      shares no code with the library, and 32 queries against the fp64 oracle (tie-aware).
+* C4  per-GPU shard at 8 GPUs: 1.25M x 1024 fp16, 1024 queries, top-100, same check.
+* C2  dense side at its exact shape (100k x 768 bf16, 256 queries, top-50) against the fp64 oracle for
+      every query; the whole hybrid (BM25 top-50 + dense top-50 -> RRF top-10 and top-50) over 100k
+      documents against the oracles end to end.
+* ``ragarc_normalize_cast`` / ``ragarc_normalize_split3`` directly: zero rows, bit-level facts.
+
+Tolerances: identical storage-dtype inputs, fp32 accumulation on both sides -> scores within
+1e-5 * max(1,|s|); ids exact wherever neighbouring reference scores are further apart than that.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25 as obm25
+from oracle import dense as odense
+from oracle import rrf as orrf
+from oracle.compare import check_topk_against_scores
+from rag_arc_b200 import _native as N
+from rag_arc_b200 import ops, synth
+from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _torch_reference_topk(x, q, k, chunk=1 << 19):
+    """fp32 matmul + topk over row chunks, merged with a stable sort (ties -> lowest row id)."""
+    nq = q.shape[0]
+    best_s = torch.full((nq, k), float("-inf"), device=x.device)
+    best_i = torch.full((nq, k), -1, dtype=torch.int64, device=x.device)
+    qf = q.float()
+    for s0 in range(0, x.shape[0], chunk):
+        e0 = min(x.shape[0], s0 + chunk)
+        sc = qf @ x[s0:e0].float().T
+        ts, ti = torch.topk(sc, min(k, e0 - s0), dim=1)
+        cs = torch.cat([best_s, ts], 1); ci = torch.cat([best_i, ti + s0], 1)
+        # order by (score desc, id asc): stable sort by id first, then by score
+        o1 = torch.argsort(ci, dim=1, stable=True)
+        cs, ci = cs.gather(1, o1), ci.gather(1, o1)
+        o2 = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :k]
+        best_s, best_i = cs.gather(1, o2), ci.gather(1, o2)
+    return best_s, best_i
+
+
+def _assert_matches_reference(scores, ids, ref_s, ref_i, what):
+    tol = TOL * ref_s.abs().clamp(min=1.0)
+    assert bool(((scores - ref_s).abs() <= tol).all()), f"{what}: scores differ by more than 1e-5"
+    same = ids == ref_i
+    if bool(same.all()):
+        return 1.0
+    # a differing id is only legal inside a group of reference scores closer than the tolerance:
+    # the row we returned must carry (within tol) the reference score of that position, and it must
+    # appear somewhere in the reference list or tie with the k-th score
+    bad_q, bad_j = (~same).nonzero(as_tuple=True)
+    for qi, j in zip(bad_q.tolist(), bad_j.tolist()):
+        t = float(tol[qi, j])
+        near = ((ref_s[qi] - ref_s[qi, j]).abs() <= 2 * t)
+        assert int(near.sum()) >= 2 or j == ids.shape[1] - 1, f"{what}: q{qi} rank {j}: id {int(ids[qi, j])} vs {int(ref_i[qi, j])} without a tie"
+    return float(same.float().mean())
+
+
+def _oracle_subset(x, q, scores, ids, k, rows, what):
+    """fp64 adjudication of a few queries over ALL rows (scores computed chunk by chunk on the host)."""
+    rows = list(rows)
+    Qs = q[rows].float().cpu().numpy().astype(np.float64)
+    S = np.empty((len(rows), x.shape[0]), np.float64)
+    for s0 in range(0, x.shape[0], 100_000):
+        e0 = min(x.shape[0], s0 + 100_000)
+        S[:, s0:e0] = Qs @ x[s0:e0].float().cpu().numpy().astype(np.float64).T
+    for j, qi in enumerate(rows):
+        check_topk_against_scores(ids[qi].cpu().numpy(), scores[qi].cpu().numpy(), S[j], k, rtol=TOL, atol=TOL, what=f"{what} q{qi}")
+
+
+def test_c3_every_query_against_every_row(dev):
+    n, d, nq, k = 1_000_000, 768, 1024, 100
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev)
+    q, planted = synth.dense_queries_cuda(x, nq)
+    scores, ids, path = ops.dense_topk(x, q, k, return_path=True)
+    assert path == N.DENSE_TCGEN05
+    ref_s, ref_i = _torch_reference_topk(x, q, k)
+    frac = _assert_matches_reference(scores, ids, ref_s, ref_i, "c3")
+    assert frac > 0.9999 and bool((ids[:, 0] == planted).all())
+    _oracle_subset(x, q, scores, ids, k, range(0, nq, 32), "c3 fp64")
+
+
+def test_c4_shard_shape_fp16_d1024(dev):
+    n, d, nq, k = 1_250_000, 1024, 1024, 100
+    x = synth.dense_corpus_cuda(n, d, torch.float16, dev)
+    q, planted = synth.dense_queries_cuda(x, nq)
+    scores, ids, path = ops.dense_topk(x, q, k, return_path=True)
+    assert path == N.DENSE_TCGEN05
+    ref_s, ref_i = _torch_reference_topk(x, q, k)
+    frac = _assert_matches_reference(scores, ids, ref_s, ref_i, "c4 shard")
+    assert frac > 0.9999 and bool((ids[:, 0] == planted).all())
+    _oracle_subset(x[:250_000].contiguous(), q, *ops.dense_topk(x[:250_000].contiguous(), q, k), k, (0, 511, 1023), "c4 fp64")
+
+
+def test_c2_dense_exact_shape_and_hybrid_100k_end_to_end(dev):
+    n, d, nq, k = 100_000, 768, 256, 50
+    x = synth.dense_corpus_cuda(n, d, torch.bfloat16, dev)
+    q, planted = synth.dense_queries_cuda(x, nq)
+    ds, di = ops.dense_topk(x, q, k)
+    assert bool((di[:, 0] == planted).all())
+    # dense: every query against the fp64 oracle (full score vectors)
+    X64 = x.float().cpu().numpy().astype(np.float64)
+    Q64 = q.float().cpu().numpy().astype(np.float64)
+    S = Q64 @ X64.T                                            # [256, 100k] fp64
+    dense_ref = []
+    for qi in range(nq):
+        check_topk_against_scores(di[qi].cpu().numpy(), ds[qi].cpu().numpy(), S[qi], k, rtol=TOL, atol=TOL, what=f"c2 dense q{qi}")
+        dense_ref.append(np.lexsort((np.arange(n), -S[qi]))[:k])
+    # sparse: bit-exact fp64 against the CSR oracle for every query
+    toks, offs = synth.bm25_corpus_tokens(n)
+    qtok = synth.bm25_queries_tokens(toks, offs, nq)
+    idx = Bm25Index.from_token_ids(toks, offs, device=dev)
+    qt, ql = idx.encode_query_ids(qtok)
+    bs, bi = ops.bm25_topk(idx, qt, ql, k)
+    ref = obm25.Bm25Csr([toks[offs[i]:offs[i + 1]].tolist() for i in range(n)])
+    bm_ref = []
+    for qi in range(nq):
+        want = ref.get_scores(qtok[qi].tolist())
+        top = obm25.stable_topk(want, k)
+        assert bi[qi].cpu().tolist() == top.tolist(), f"c2 bm25 ids q{qi}"
+        assert np.array_equal(bs[qi].cpu().numpy().view(np.uint64), want[top].view(np.uint64)), f"c2 bm25 scores q{qi}"
+        bm_ref.append(top)
+    # fusion: RRF over (BM25 list, dense list), top-10 and top-50, against the oracle fed with OUR lists
+    # (bit-exact) and - wherever our dense list equals the fp64 oracle's exactly - end to end
+    lists = torch.stack([bi.to(torch.int32), di.to(torch.int32)], 0).contiguous()
+    di_h, bi_h = di.cpu().numpy(), bi.cpu().numpy()
+    for top_k in (10, 50):
+        fi, fs, fc = ops.rrf_fuse(lists, top_k)
+        fi, fs, fc = fi.cpu().numpy(), fs.cpu().numpy(), fc.cpu().numpy()
+        end_to_end = 0
+        for qi in range(nq):
+            want_ids, want_sc = orrf.rrf_fuse_ids([bi_h[qi].tolist(), di_h[qi].tolist()], top_k)
+            assert fi[qi, :fc[qi]].tolist() == want_ids and fs[qi, :fc[qi]].tolist() == want_sc, f"c2 rrf q{qi} top{top_k}"
+            if np.array_equal(di_h[qi], dense_ref[qi]):
+                e2e_ids, _ = orrf.rrf_fuse_ids([bm_ref[qi].tolist(), dense_ref[qi].tolist()], top_k)
+                assert fi[qi, :fc[qi]].tolist() == e2e_ids
+                end_to_end += 1
+        assert end_to_end >= 0.98 * nq          # near-ties at 1e-5 may reorder a handful of dense lists
+
+
+def test_normalize_cast_directly(dev):
+    """faiss.normalize_L2 semantics of ragarc_normalize_cast: zero rows come back untouched (bit for
+    bit, in every output dtype), rows with one non-zero element normalise to exactly +-1, general rows
+    agree with the oracle to a few ulp (the row sum is reduced in a different order), the half-precision outputs are the round-to-nearest casts of the
+    fp32 output, and normalize=0 is a pure cast."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((257, 96), generator=g)
+    x[5] = 0.0
+    x[200] = 0.0
+    x[7] = 0.0; x[7, 13] = -3.5
+    x[9] = 0.0; x[9, 95] = 1e-15                               # tiny but non-zero: still normalised
+    xd = x.to(dev)
+    f32 = ops.normalize_cast(xd, torch.float32, True)
+    assert torch.equal(f32[5].cpu(), torch.zeros(96)) and torch.equal(f32[200].cpu(), torch.zeros(96))
+    assert f32[7, 13].item() == -1.0 and float(f32[7].abs().sum()) == 1.0
+    assert f32[9, 95].item() == pytest.approx(1.0, rel=1e-6)
+    want = x.numpy().copy()
+    odense.normalize_L2(want)
+    got = f32.cpu().numpy()
+    ulp = np.spacing(np.abs(want).astype(np.float32))
+    assert (np.abs(got - want) <= 4 * ulp + 1e-30).all()
+    assert np.allclose(np.linalg.norm(got[[i for i in range(257) if i not in (5, 200)]], axis=1), 1.0, atol=1e-6)
+    for dt in (torch.bfloat16, torch.float16):
+        half = ops.normalize_cast(xd, dt, True)
+        assert torch.equal(half, f32.to(dt)), dt               # same fp32 value, rounded once
+        assert torch.equal(half[5].float().cpu(), torch.zeros(96))
+        assert torch.equal(ops.normalize_cast(xd, dt, False), xd.to(dt))
+    assert torch.equal(ops.normalize_cast(xd, torch.float32, False), xd)
+    # in place (dst aliases src) is allowed for fp32 output
+    y = xd.clone()
+    ops.normalize_cast(y, torch.float32, True, out=y)
+    assert torch.equal(y, f32)
+
+
+def test_normalize_split3_directly(dev):
+    """Three bf16 planes: v1 = bf16(v), v2 = bf16(v - v1), v3 = bf16(v - v1 - v2), computed on the
+    (optionally normalised) fp32 value; zero rows give three zero planes; the planes reproduce the
+    fp32 value to 2^-22 relative and v1 is exactly the bf16 rounding."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((130, 64), generator=g) * 3.0
+    x[0] = 0.0
+    x[64] = 0.0
+    xd = x.to(dev)
+    for normalize in (False, True):
+        base = ops.normalize_cast(xd, torch.float32, normalize)
+        planes = ops.normalize_split3(xd, normalize).view(130, 3, 64)
+        v1, v2, v3 = planes[:, 0].float(), planes[:, 1].float(), planes[:, 2].float()
+        assert torch.equal(planes[:, 0], base.to(torch.bfloat16))
+        assert torch.equal(planes[:, 1], (base - v1).to(torch.bfloat16))
+        assert torch.equal(planes[:, 2], (base - v1 - v2).to(torch.bfloat16))
+        assert float(planes[0].float().abs().sum()) == 0.0 and float(planes[64].float().abs().sum()) == 0.0
+        rec = v1 + v2 + v3
+        assert bool(((rec - base).abs() <= 2.0 ** -22 * base.abs() + 1e-38).all())

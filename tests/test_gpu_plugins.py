@@ -67,6 +67,63 @@ def test_vector_store_matches_reference_faiss_store_golden(dev, metric):
             assert [int(d.id) for d in docs] == case["ids"]
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_vector_store_l2_metric_matches_reference_golden(dev, dtype, tmp_path):
+    """tests/golden/dense_l2_small.json: the reference's FaissVectorStore(metric="l2") run live
+    (squared distances ascending, 1 - d/sqrt(2) relevance, MMR on raw dot products).  fp32 storage must
+    reproduce ids and distances (1e-5); bf16 storage is checked against the oracle on its own rounded
+    rows (the golden's fp32 distances differ by the storage rounding, north_star: 1e-2 relative)."""
+    from oracle import dense as odense
+    with open(os.path.join(GOLD, "dense_l2_small.json")) as f:
+        l2 = json.load(f)
+    gold, emb = _dense_fixture()
+    n = len(gold["texts"])
+    for normalize in (False, True):
+        store = B200VectorStore.from_texts(gold["texts"], emb, ids=[str(i) for i in range(n)], metric="l2",
+                                           normalize_L2=normalize, dtype=dtype, device=dev)
+        assert store.index.l2 and store.ntotal == n
+        ref_index = odense.IndexFlatL2(store.index.d)
+        ref_index.add(store.index.rows[:n].float().cpu().numpy())          # the rows as stored (rounded for bf16)
+        for case in l2["cases"]:
+            if case["normalize_L2"] != normalize:
+                continue
+            q = gold["queries"][case["query"]]
+            if case["kind"] == "similarity_with_score":
+                res = store.similarity_search_with_score(q, case["k"])
+                got_d = [s for _, s in res]
+                assert got_d == sorted(got_d)
+                if dtype == "float32":
+                    assert [int(d.id) for d, _ in res] == case["ids"]
+                    assert np.allclose(got_d, case["scores"], rtol=1e-5, atol=2e-5)
+                else:
+                    qv = store.index.prepare_plain(np.asarray([emb.embed_query(q)], np.float32)).float().cpu().numpy()
+                    D, I = ref_index.search(qv, case["k"])
+                    assert np.allclose(got_d, D[0], rtol=1e-5, atol=2e-5)
+                    assert [int(d.id) for d, _ in res] == [int(i) for i in I[0]] or np.allclose(got_d, D[0], atol=1e-6)
+                    assert np.allclose(got_d, case["scores"], rtol=3e-2, atol=3e-2)
+            elif case["kind"] == "relevance" and dtype == "float32":
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    rel = store.similarity_search_with_relevance_scores(q, k=6)
+                assert [int(d.id) for d, _ in rel] == case["ids"]
+                assert np.allclose([s for _, s in rel], case["relevance"], rtol=1e-5, atol=2e-5)
+            elif case["kind"] == "mmr" and dtype == "float32":
+                docs = store.max_marginal_relevance_search(q, k=3, fetch_k=10, lambda_mult=0.5)
+                assert [int(d.id) for d in docs] == case["ids"]
+        if dtype == "float32" and not normalize:
+            # delete + persistence keep the augmented matrix in step with the rows
+            before = store.similarity_search_with_score(gold["queries"][0], 5)
+            store.save_local(str(tmp_path / "l2"))
+            again = B200VectorStore.load_local(str(tmp_path / "l2"), emb, device=dev)
+            assert again.metric == "l2" and again.index.l2
+            assert [(d.id, s) for d, s in again.similarity_search_with_score(gold["queries"][0], 5)] == [(d.id, s) for d, s in before]
+            first = before[0][0].id
+            assert store.delete([first]) is True
+            after = store.similarity_search_with_score(gold["queries"][0], 4)
+            assert [d.id for d, _ in after] == [d.id for d, _ in before[1:]]
+            assert np.allclose([s for _, s in after], [s for _, s in before[1:]], rtol=1e-6, atol=1e-6)
+
+
 def test_vector_store_bookkeeping_delete_persist_batch(dev, tmp_path):
     emb = HashEmbeddings(64)
     texts = [f"alpha beta {i} gamma{i % 7}" for i in range(200)]
@@ -132,8 +189,12 @@ def test_float32x3_store_matches_fp32_golden(dev, tmp_path):
     of 64 there, so use the hash embedding at d=128 and compare with the plain fp32 store)."""
     emb = HashEmbeddings(128)
     texts = [f"alpha beta {i} gamma{i % 11} delta{i % 5}" for i in range(400)]
-    a = B200VectorStore.from_texts(texts, emb, ids=[str(i) for i in range(400)], dtype="float32", device=dev)
+    a = B200VectorStore.from_texts(texts, emb, ids=[str(i) for i in range(400)], dtype="float32_exact", device=dev)
     b = B200VectorStore.from_texts(texts, emb, ids=[str(i) for i in range(400)], dtype="float32x3", device=dev)
+    auto = B200VectorStore.from_texts(texts, emb, ids=[str(i) for i in range(400)], dtype="float32", device=dev)
+    assert not a.index.x3 and b.index.x3 and auto.index.x3          # the default picks the tensor-core path at d % 64 == 0
+    odd = B200VectorStore.from_texts(texts[:20], HashEmbeddings(48), dtype="float32", device=dev)
+    assert not odd.index.x3                                          # ... and the fp32 FMA path otherwise
     for q in (texts[3], texts[77], "gamma4 delta2 beta", "unrelated words"):
         ra = a.similarity_search_with_score(q, 8); rb = b.similarity_search_with_score(q, 8)
         assert [d.id for d, _ in ra] == [d.id for d, _ in rb]
@@ -429,3 +490,58 @@ def test_load_local_keeps_reference_rows_bitwise_and_validates_the_folder(dev, t
         formats.load_reference_sidecar(str(tmp_path / "evil.pkl"))
     with pytest.raises(ValueError, match="must match number of texts"):
         ok.add_embeddings(["a", "b"], vec[:3], None)
+
+
+def test_huggingface_embeddings_same_constructor_as_the_reference(dev, tmp_path):
+    """HuggingFaceEmbeddings(model_name=, cache_folder=, model_kwargs=, encode_kwargs=, multi_process=,
+    show_progress_bar=) - the reference's constructor (huggingface.py:67-98) - over a tiny random BERT
+    saved in sentence-transformers layout: pooling mode and the Normalize module are read from the
+    model directory, prompts are prepended, newlines replaced (:116), results are lists of floats
+    (:134) equal to the oracle's pooling of the same hidden states."""
+    from transformers import BertConfig, BertModel, BertTokenizer
+    from oracle import pool as opool
+    from rag_arc_b200.core.file_management.embeddings.huggingface import HuggingFaceEmbeddings
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [f"w{i}" for i in range(40)] + ["query", ":", "hello", "world"]
+    mdir = tmp_path / "tiny"
+    mdir.mkdir()
+    (mdir / "vocab.txt").write_text("\n".join(vocab))
+    BertTokenizer(str(mdir / "vocab.txt")).save_pretrained(str(mdir))
+    torch.manual_seed(0)
+    BertModel(BertConfig(vocab_size=len(vocab), hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
+                         intermediate_size=64, max_position_embeddings=64)).save_pretrained(str(mdir))
+    texts = ["hello world w1 w2", "w3\nw4 w5 w6 w7 w8", "w9"]
+
+    def reference_rows(emb, prepared, mode, normalize):
+        enc = emb._client.tokenizer(prepared, padding=True, truncation=True, max_length=512, return_tensors="pt").to(emb._client.model.device)
+        with torch.no_grad():
+            hidden = emb._client.model(**enc).last_hidden_state
+        return opool.pool_normalize(hidden.float().cpu().numpy(), enc["attention_mask"].cpu().numpy(), mode, normalize)
+
+    mk = {"device": str(dev), "torch_dtype": "float32"}
+    # plain transformers checkpoint: mean pooling, normalisation only on request
+    e1 = HuggingFaceEmbeddings(model_name=str(mdir), model_kwargs=mk, encode_kwargs={"normalize_embeddings": True, "batch_size": 2})
+    got = e1.embed_documents(texts)
+    assert isinstance(got, list) and isinstance(got[0], list) and isinstance(got[0][0], float) and len(got[0]) == 32
+    want = reference_rows(e1, [t.replace("\n", " ") for t in texts], "mean", True)
+    assert np.allclose(np.asarray(got, np.float32), want, rtol=1e-5, atol=1e-6)
+    assert np.allclose(e1.embed_query(texts[0]), want[0], rtol=1e-5, atol=1e-6)
+    e2 = HuggingFaceEmbeddings(model_name=str(mdir), model_kwargs=mk)
+    assert np.allclose(np.asarray(e2.embed_documents(texts), np.float32), reference_rows(e2, [t.replace("\n", " ") for t in texts], "mean", False), rtol=1e-5, atol=1e-6)
+    # sentence-transformers layout: CLS pooling + Normalize module, prompts
+    (mdir / "1_Pooling").mkdir()
+    (mdir / "1_Pooling" / "config.json").write_text(json.dumps({"word_embedding_dimension": 32, "pooling_mode_cls_token": True,
+                                                                  "pooling_mode_mean_tokens": False}))
+    (mdir / "modules.json").write_text(json.dumps([
+        {"idx": 0, "name": "0", "path": "", "type": "sentence_transformers.models.Transformer"},
+        {"idx": 1, "name": "1", "path": "1_Pooling", "type": "sentence_transformers.models.Pooling"},
+        {"idx": 2, "name": "2", "path": "2_Normalize", "type": "sentence_transformers.models.Normalize"}]))
+    e3 = HuggingFaceEmbeddings(model_name=str(mdir), model_kwargs={**mk, "prompts": {"query": "query : "}, "default_prompt_name": "query"},
+                               multi_process=True, show_progress_bar=False)
+    assert e3.pooling == "cls"
+    want3 = reference_rows(e3, ["query : " + t.replace("\n", " ") for t in texts], "cls", True)
+    assert np.allclose(np.asarray(e3.embed_documents(texts), np.float32), want3, rtol=1e-5, atol=1e-6)
+    assert e3.embed_documents_tensor(texts).shape == (3, 32)
+    with pytest.raises(ValueError):
+        HuggingFaceEmbeddings(model_name=str(mdir), pooling="mean")          # extra="forbid" in the reference
+    with pytest.raises(ValueError):
+        HuggingFaceEmbeddings(model_name=str(mdir), model_kwargs={**mk, "default_prompt_name": "nope"})

@@ -85,3 +85,12 @@ def test_load_local_imports_reference_folder():
 
 def test_load_local_bitwise_rows_and_folder_validation(tmp_path):
     T.test_load_local_keeps_reference_rows_bitwise_and_validates_the_folder(CPU, tmp_path)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_vector_store_l2_metric_host_logic(dtype, tmp_path):
+    T.test_vector_store_l2_metric_matches_reference_golden(CPU, dtype, tmp_path)
+
+
+def test_huggingface_embeddings_host_logic(tmp_path):
+    T.test_huggingface_embeddings_same_constructor_as_the_reference(CPU, tmp_path)
