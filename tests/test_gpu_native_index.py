@@ -72,7 +72,7 @@ def test_remove_renumbers_like_faiss_remove_ids(dev):
 def test_bad_arguments_fail_loudly(dev):
     from rag_arc_b200._native import RagArcError
     with pytest.raises(ValueError):
-        NativeFlatIndex(64, "float32", "l2")
+        NativeFlatIndex(64, "float32", "hamming")
     ix = NativeFlatIndex(64, "float32", "ip")
     ix.add(np.zeros((4, 64), np.float32))
     with pytest.raises(RagArcError):
