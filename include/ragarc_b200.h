@@ -258,6 +258,29 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
                      int64_t* out_ids /* [nq,k] */, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Host-side query encoding for ragarc_bm25_topk / ragarc_bm25_scores: the batch form of what the
+ * reference does per query in Python - preprocess_func(query) = query.split() (core/retrieval/
+ * bm25.py:16-25,:302) and rank_bm25's per-token dictionary lookups (inside get_scores, :306).
+ * ragarc_vocab_create copies n_tokens vocabulary strings (token i = tokens_blob[offsets[i],
+ * offsets[i+1]), UTF-8, id = i; a repeated string keeps its first id).  ragarc_vocab_encode_split
+ * tokenises text q = texts_blob[offsets[q], offsets[q+1]) on whitespace exactly as Python's
+ * str.split() does (every character with str.isspace(), UTF-8 aware), looks every token up and
+ * writes out_terms[q, 0..tmax) (-1 = out of vocabulary, and padding) and out_len[q] = min(tokens, tmax);
+ * *max_len (may be NULL) = the longest query's token count - call again with a larger tmax if it
+ * exceeds tmax.  All pointers are HOST memory (use pinned buffers to overlap the upload). */
+typedef struct ragarc_vocab ragarc_vocab_t;
+int ragarc_vocab_create(const char* tokens_blob, const int64_t* offsets, int64_t n_tokens, ragarc_vocab_t** out);
+int ragarc_vocab_free(ragarc_vocab_t* vocab);
+int64_t ragarc_vocab_size(const ragarc_vocab_t* vocab);
+int ragarc_vocab_encode_split(const ragarc_vocab_t* vocab, const char* texts_blob, const int64_t* offsets,
+                              int nq, int tmax, int32_t* out_terms_host, int32_t* out_len_host,
+                              int* max_len_host);
+/* Same, the nq texts given as ONE buffer of blob_bytes bytes separated by NUL bytes (what
+ * "\0".join(texts).encode() produces: one allocation on the caller's side instead of nq). */
+int ragarc_vocab_encode_split0(const ragarc_vocab_t* vocab, const char* texts_blob, int64_t blob_bytes,
+                               int nq, int tmax, int32_t* out_terms_host, int32_t* out_len_host,
+                               int* max_len_host);
+
 /* Doc-range sharded BM25 (multi-GPU): every shard scores its own documents with the GLOBAL idf and
  * average length (the reference computes both over the whole corpus, bm25.py:218) and reports global
  * doc ids; this merges the per-shard results scores/ids [n_lists, nq, k_in] (ids -1 = padding) into

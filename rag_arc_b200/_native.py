@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RAGARC_LIB: load another build of the same library (e.g. one compiled with -DRAGARC_TC_STATS_BUILD)
 LIB_PATH = os.environ.get("RAGARC_LIB") or os.path.join(_HERE, "libragarc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu"]
+SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu", "vocab.cu"]
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
 METRIC_IP, METRIC_COSINE, METRIC_L2 = 0, 1, 2
@@ -31,7 +31,8 @@ EXPORTS = [
     "ragarc_l2_aug_dim", "ragarc_l2_augment", "ragarc_l2_distances",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
-    "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
+    "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_vocab_create", "ragarc_vocab_free", "ragarc_vocab_size",
+    "ragarc_vocab_encode_split", "ragarc_vocab_encode_split0", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
     "ragarc_adjacent_cosine_distance", "ragarc_yes_no_score",
     "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
     "ragarc_index_remove", "ragarc_index_ntotal", "ragarc_index_dim", "ragarc_index_rows",
@@ -115,6 +116,11 @@ def _load():
         "ragarc_sharded_search": (c_int, [P, P, c_int, c_int, P, P]),
         "ragarc_sharded_ntotal": (c_int64, [P]),
         "ragarc_bm25_merge_topk": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
+        "ragarc_vocab_create": (c_int, [P, P, c_int64, ctypes.POINTER(ctypes.c_void_p)]),
+        "ragarc_vocab_free": (c_int, [P]),
+        "ragarc_vocab_size": (c_int64, [P]),
+        "ragarc_vocab_encode_split": (c_int, [P, P, P, c_int, c_int, P, P, ctypes.POINTER(c_int)]),
+        "ragarc_vocab_encode_split0": (c_int, [P, P, c_int64, c_int, c_int, P, P, ctypes.POINTER(c_int)]),
         "ragarc_bm25_topk": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
                                      P, c_size_t, P]),
         "ragarc_rrf_fuse": (c_int, [P, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),

@@ -73,6 +73,12 @@ class B200BM25Okapi:
         qt, ql = self.index.encode_queries(queries)
         return ops.bm25_topk(self.index, qt, ql, k)
 
+    def get_batch_topk_texts(self, texts: Sequence[str], k: int):
+        """Same for raw query strings under the default whitespace tokeniser: split + vocabulary lookup
+        + packing happen in one library call (``ragarc_vocab_encode_split``), not per token in Python."""
+        qt, ql = self.index.encode_texts(texts)
+        return ops.bm25_topk(self.index, qt, ql, k)
+
     def __getstate__(self):
         ix = self.index
         return {"k1": self.k1, "b": self.b, "epsilon": self.epsilon, "tokenizer": self.tokenizer,
@@ -188,6 +194,9 @@ class BM25Retriever(BaseRetriever):
         if self.vectorizer is None:
             raise ValueError("BM25 vectorizer is not initialised")
         k = k or self.k
+        if (self.preprocess_func is default_preprocessing_func and hasattr(self.vectorizer, "get_batch_topk_texts")
+                and getattr(self.vectorizer, "tokenizer", None) is None and self.vectorizer.index.vocab is not None):
+            return self.vectorizer.get_batch_topk_texts(queries, k)
         return self.vectorizer.get_batch_topk([self.preprocess_func(q) for q in queries], k)
 
     def batch_rows(self, queries: List[str], k: int):

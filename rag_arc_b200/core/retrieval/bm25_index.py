@@ -18,6 +18,20 @@ import numpy as np
 import torch
 
 
+class _VocabHandle:
+    """Owns a ``ragarc_vocab_t`` (freed with the index)."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            from ... import _native as N
+            N.lib.ragarc_vocab_free(self.h)
+        except Exception:
+            pass
+
+
 class Bm25Index:
     def __init__(self, *, vocab: Optional[Dict[str, int]], indptr: np.ndarray, post_doc: np.ndarray,
                  post_tf: np.ndarray, doc_len: np.ndarray, k1: float, b: float, epsilon: float,
@@ -137,6 +151,65 @@ class Bm25Index:
                    doc_len=lens, k1=k1, b=b, epsilon=epsilon, device=device)
 
     # -- queries -------------------------------------------------------------------------------
+    def _native_vocab(self):
+        """The vocabulary as a C++ hash table inside the library (built once, on first use)."""
+        v = getattr(self, "_vocab_handle", None)
+        if v is None:
+            import ctypes
+            from ... import _native as N
+            toks = [None] * len(self.vocab)
+            for tok, ti in self.vocab.items():
+                toks[ti] = tok.encode("utf-8")
+            offs = np.zeros(len(toks) + 1, np.int64)
+            np.cumsum([len(t) for t in toks], out=offs[1:])
+            blob = b"".join(toks)
+            h = ctypes.c_void_p()
+            N.check(N.lib.ragarc_vocab_create(blob, offs.ctypes.data, len(toks), ctypes.byref(h)), "vocab_create")
+            v = self._vocab_handle = _VocabHandle(h)
+        return v.h
+
+    def encode_texts(self, texts: Sequence[str], tmax: int = 32):
+        """Whitespace-tokenise (``str.split()`` semantics), look up and pack a batch of query strings in
+        one library call (``ragarc_vocab_encode_split``) -> the ``(q_terms, q_len)`` device tensors
+        ``encode_queries`` returns for ``[t.split() for t in texts]``.  The packed arrays are written
+        straight into pinned staging buffers and uploaded asynchronously."""
+        import ctypes
+        from ... import _native as N
+        h = self._native_vocab()
+        nq = len(texts)
+        joined = "\0".join(texts)
+        nul_ok = joined.count("\0") == max(nq - 1, 0)           # no query contains a NUL itself (else: offsets form)
+        if nul_ok:
+            blob, offs = joined.encode("utf-8"), None
+        else:
+            enc = [t.encode("utf-8") for t in texts]
+            offs = np.zeros(nq + 1, np.int64)
+            np.cumsum([len(b) for b in enc], out=offs[1:])
+            blob = b"".join(enc)
+        cuda = self.device is not None and self.device.type == "cuda"
+        while True:
+            stage = getattr(self, "_enc_stage", None)
+            if stage is None or stage[0].shape[0] < nq or stage[0].shape[1] != tmax:
+                terms = torch.empty((max(nq, 1), tmax), dtype=torch.int32)
+                lens = torch.empty((max(nq, 1),), dtype=torch.int32)
+                if cuda:
+                    terms, lens = terms.pin_memory(), lens.pin_memory()
+                stage = self._enc_stage = (terms, lens)
+            longest = ctypes.c_int(0)
+            if nul_ok:
+                N.check(N.lib.ragarc_vocab_encode_split0(h, blob, len(blob), nq, tmax, stage[0].data_ptr(),
+                                                         stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split0")
+            else:
+                N.check(N.lib.ragarc_vocab_encode_split(h, blob, offs.ctypes.data, nq, tmax, stage[0].data_ptr(),
+                                                        stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split")
+            if longest.value <= tmax:
+                break
+            tmax = 1 << (longest.value - 1).bit_length()                  # a longer query than the staging row: grow, redo
+        width = max(1, longest.value)
+        q_terms = stage[0][:nq, :width].to(self.device, non_blocking=True).contiguous()
+        q_len = stage[1][:nq].to(self.device, non_blocking=True)
+        return q_terms, q_len
+
     def encode_queries(self, queries: Iterable[Sequence[str]]):
         """Token lists -> (q_terms int32 [nq,tmax] with -1 for out-of-vocabulary tokens, q_len)."""
         get = self.vocab.get

@@ -61,7 +61,8 @@ class MultiPathRetriever(BaseRetriever):
             docs = r.row_documents()
             tab = np.fromiter((keys.setdefault(d.content, len(keys)) for d in docs), np.int32, len(docs))
             tabs.append(tab)
-            tables.append(torch.from_numpy(tab).to(device))
+            # device table with one extra trailing -1: indexing it with row -1 (padding) yields key -1
+            tables.append(torch.from_numpy(np.concatenate([tab, np.array([-1], np.int32)])).to(device))
         # per retriever: key -> the LAST row holding that content (-1: not in this retriever's corpus)
         key_last_row = np.full((len(self.retrievers), max(len(keys), 1)), -1, np.int64)
         for l, tab in enumerate(tabs):
@@ -77,35 +78,40 @@ class MultiPathRetriever(BaseRetriever):
         device = torch.device(getattr(self.fusion_method, "device", "cuda"))
         _, tables = self._canonical_tables(device)
         nq = len(queries)
-        ids = torch.full((len(self.retrievers), nq, kl), -1, dtype=torch.int32, device=device)
+        L = len(self.retrievers)
+        per_list = []
         for l, r in enumerate(self.retrievers):
+            keys = None
             try:
-                if len(r.row_documents()) == 0:
-                    continue
-                rows = r.batch_rows(queries, kl).to(device)
-                valid = rows >= 0
-                keys = tables[l][rows.clamp(min=0)]
-                ids[l, :, :rows.shape[1]] = torch.where(valid, keys, torch.full_like(keys, -1))
+                if len(r.row_documents()) > 0:
+                    rows = r.batch_rows(queries, kl).to(device)
+                    # row -> content key through the device table; -1 rows (padding) stay -1: the table has a
+                    # trailing -1 entry that row -1 indexes
+                    keys = tables[l][rows]
+                    if keys.shape[1] < kl:
+                        keys = torch.nn.functional.pad(keys, (0, kl - keys.shape[1]), value=-1)
             except Exception as exc:  # noqa: BLE001
                 print(f"retriever {type(r).__name__} failed: {exc}")
-        fused_ids, _, counts = self.fusion_method.fuse_batch(ids.contiguous(), top_k)
-        fused_ids = fused_ids.cpu().numpy(); counts = counts.cpu().numpy(); ids_h = ids.cpu().numpy()
+                keys = None
+            per_list.append(keys if keys is not None else torch.full((nq, kl), -1, dtype=torch.int32, device=device))
+        ids = torch.stack(per_list, 0)
+        fused_ids, _, counts = self.fusion_method.fuse_batch(ids, top_k)
+        # one device->host transfer for everything the document lookup needs
+        packed = torch.cat([fused_ids.reshape(-1), counts.reshape(-1), ids.reshape(-1)]).cpu().numpy()
+        fused_ids = packed[:nq * top_k].reshape(nq, top_k)
+        counts = packed[nq * top_k:nq * top_k + nq]
+        ids_h = packed[nq * top_k + nq:].reshape(L, nq, kl)
         # reference semantics: the Document returned for a content string is the LAST one seen
         # while walking the lists in retriever order (Fusion.py:61) - i.e. it comes from the last
         # retriever whose list holds the key; inside one retriever duplicate contents resolve to the
         # last row carrying them
         row_docs = [r.row_documents() for r in self.retrievers]
         key_last_row = self._canon_cache[3]
-        L = len(self.retrievers)
         present = (ids_h[:, :, None, :] == fused_ids[None, :, :, None]).any(axis=3)    # [L, nq, top_k]
         last_l = (L - 1) - np.argmax(present[::-1], axis=0)                            # [nq, top_k]
         rows = key_last_row[last_l, np.clip(fused_ids, 0, None)]                       # [nq, top_k]
-        out: List[List[Document]] = []
-        for q in range(nq):
-            c = int(counts[q])
-            out.append([row_docs[l][r] if r >= 0 else None
-                        for l, r in zip(last_l[q, :c].tolist(), rows[q, :c].tolist())])
-        return out
+        ll, rr, cc = last_l.tolist(), rows.tolist(), counts.tolist()
+        return [[row_docs[l][r] if r >= 0 else None for l, r in zip(ll[q][:cc[q]], rr[q][:cc[q]])] for q in range(nq)]
 
     # ---- management --------------------------------------------------------------------------------
     def add_retriever(self, retriever: BaseRetriever):

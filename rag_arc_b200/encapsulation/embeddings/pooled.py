@@ -84,8 +84,13 @@ class TableEmbeddings(Embeddings):
 
     def embed_documents_array(self, texts: List[str]) -> np.ndarray:
         """Same vectors as one float32 ``[n,d]`` array (skips the list-of-floats round trip the
-        reference interface imposes; batched retrievers use it when present)."""
-        return np.stack([np.asarray(self.table[t], dtype=np.float32) for t in texts])
+        reference interface imposes; batched retrievers use it when present): one fancy-index gather
+        out of a matrix built on first use."""
+        if getattr(self, "_matrix", None) is None or len(self._row_of) != len(self.table):
+            keys = list(self.table)
+            self._row_of = {t: i for i, t in enumerate(keys)}
+            self._matrix = np.stack([np.asarray(self.table[t], dtype=np.float32) for t in keys]) if keys else np.zeros((0, 0), np.float32)
+        return self._matrix[np.fromiter((self._row_of[t] for t in texts), np.int64, len(texts))]
 
     def embed_query(self, text: str) -> List[float]:
         return np.asarray(self.table[text], dtype=np.float32).tolist()
