@@ -1,7 +1,7 @@
 # Builds the C-ABI library for sm_100a and the plain-C consumer; the Python side builds the same
 # library through __graft_entry__.build() / rag_arc_b200/_native.py.
 NVCC      ?= nvcc
-NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177,550
+NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177,550,128
 CSRC      := $(sort $(wildcard rag_arc_b200/csrc/*.cu))
 LIB       := rag_arc_b200/libragarc_b200.so
 
@@ -9,7 +9,7 @@ LIB       := rag_arc_b200/libragarc_b200.so
 lib: $(LIB)
 
 $(LIB): $(CSRC) rag_arc_b200/csrc/common.cuh include/ragarc_b200.h
-	$(NVCC) $(NVCCFLAGS) -shared $(CSRC) -o $@
+	$(NVCC) $(NVCCFLAGS) -shared $(CSRC) -o $@ -ldl
 
 # tests/c/index_smoke.c: needs a B200 to pass; without one it exits 2 with RAGARC_ERR_CUDA
 ctest: $(LIB)

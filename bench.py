@@ -637,7 +637,7 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
         if e2e_pipe_ms < e2e_ms:
             e2e_ms, e2e_api = e2e_pipe_ms, pipe_api
     # the plain C ABI with HOST buffers and no torch on the path (1 GPU)
-    cabi_ms = None
+    cabi_ms = cabi_pageable_ms = None
     if world == 1 and n_local * w["dim"] * 2 < 20e9:
         import ctypes
         h = ctypes.c_void_p()
@@ -647,22 +647,31 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
             chunk = store.index.rows[a:min(n_local, a + 131072)].float()
             N.check(N.lib.ragarc_index_add(h, chunk.data_ptr(), chunk.shape[0], 0, None), "index_add")
         torch.cuda.synchronize()
-        q_np = q_host.numpy()
-        D = np.empty((batch, k), np.float32); I = np.empty((batch, k), np.int64)
+        from rag_arc_b200.native_index import pinned_array
         n_cabi = max(5, min(steps, 50))
-        for it in range(3 + n_cabi):
-            if it == 3:
-                t0 = time.perf_counter()
-            N.check(N.lib.ragarc_index_search(h, q_np.ctypes.data, batch, k, D.ctypes.data, I.ctypes.data, 1, None),
-                    "index_search")
-        cabi_ms = (time.perf_counter() - t0) * 1e3 / n_cabi
-        assert (I[:, 0] == res_ids_host[:, 0].numpy()).all()
+        cabi = {}
+        for kind in ("pageable", "pinned"):
+            if kind == "pageable":
+                q_np = np.array(q_host.numpy(), copy=True)
+                D = np.empty((batch, k), np.float32); I = np.empty((batch, k), np.int64)
+            else:           # buffers from ragarc_host_alloc: direct DMA, no staging through the driver
+                q_np = pinned_array((batch, w["dim"]), np.float32); q_np[:] = q_host.numpy()
+                D = pinned_array((batch, k), np.float32); I = pinned_array((batch, k), np.int64)
+            for it in range(3 + n_cabi):
+                if it == 3:
+                    t0 = time.perf_counter()
+                N.check(N.lib.ragarc_index_search(h, q_np.ctypes.data, batch, k, D.ctypes.data, I.ctypes.data, 1, None),
+                        "index_search")
+            cabi[kind] = (time.perf_counter() - t0) * 1e3 / n_cabi
+            assert (I[:, 0] == res_ids_host[:, 0].numpy()).all()
+        cabi_ms = cabi["pinned"]
+        cabi_pageable_ms = cabi["pageable"]
         N.lib.ragarc_index_free(h)
     res["e2e"] = {"value": steps * batch / (e2e_ms * 1e-3), "unit": "queries/s",
                   "h2d_bytes_per_step": batch * w["dim"] * 4 * world, "d2h_bytes_per_step": batch * k * 12,
                   "h2d_bytes_per_step_per_rank": batch * w["dim"] * 4, "d2h_bytes_per_step_per_rank": n_own * k * 12,
                   "ms_per_step": e2e_ms / steps, "sync_ms_per_step": e2e_sync_ms / steps, "api": e2e_api,
-                  "cabi_host_call_ms": cabi_ms}
+                  "cabi_host_call_ms": cabi_ms, "cabi_host_call_pageable_ms": cabi_pageable_ms}
     return res, (store, q32)
 
 

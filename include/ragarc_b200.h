@@ -117,6 +117,13 @@ int ragarc_dense_topk(const void* corpus, int64_t n, int d, int dtype, const voi
  * mutex + GPU ordering across streams); different indexes are independent.
  * Search results follow ragarc_dense_topk (descending score, ties by ascending row, -1 padding).
  */
+/* Page-locked host memory for the host-buffer forms below (cudaHostAlloc / cudaFreeHost): with
+ * pinned query and result buffers the copies of ragarc_index_search are direct DMA transfers
+ * (3 MB of fp32 queries in ~60 us over PCIe 5) instead of being staged through the driver's own
+ * bounce buffers, which costs several hundred microseconds per call for pageable memory. */
+int ragarc_host_alloc(size_t bytes, void** out_host);
+int ragarc_host_free(void* host);
+
 typedef struct ragarc_index ragarc_index_t;
 int ragarc_index_create(int d, int dtype, int metric, ragarc_index_t** out);
 int ragarc_index_free(ragarc_index_t* index);
@@ -170,6 +177,30 @@ int ragarc_l2_augment(const float* src, void* dst, int64_t n, int d, int dst_dty
                       int normalize, float* sqnorm_out, void* stream);
 int ragarc_l2_distances(float* scores, const void* queries_aug, int dtype, int nq, int k, int d,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One process per GPU, NCCL between them (the reference has no distributed code).
+ * A communicator is created either from a unique id the host distributes to its ranks
+ * (ragarc_comm_unique_id on one rank, ragarc_comm_init_rank on every rank with its CUDA device
+ * current) or, for one process driving several GPUs, by ragarc_comm_init_all.  NCCL is bound at
+ * run time (libnccl.so.2, the copy already loaded into the process is reused); without it the calls
+ * fail with RAGARC_ERR_CUDA.  ragarc_comm_nccl_version() returns NCCL's version code (0 = not loadable).
+ * ragarc_sharded_topk: every rank holds a contiguous row shard (id_base = global id of its first
+ * row) and the same queries; local fused scoring + selection -> ncclAllGather of the [nq,k] packed
+ * keys -> merge; every rank gets the global result, identical to the single-GPU one for any number
+ * of ranks.  Collective: all ranks must call it with the same nq and k, on their own streams. */
+typedef struct ragarc_comm ragarc_comm_t;
+int ragarc_comm_nccl_version(void);
+int ragarc_comm_unique_id(char* out128_host);
+int ragarc_comm_init_rank(const char* id128_host, int nranks, int rank, ragarc_comm_t** out);
+int ragarc_comm_init_all(int ndev, const int* devices, ragarc_comm_t** out_comms);
+int ragarc_comm_free(ragarc_comm_t* comm);
+int ragarc_comm_rank(const ragarc_comm_t* comm);
+int ragarc_comm_nranks(const ragarc_comm_t* comm);
+size_t ragarc_sharded_topk_workspace_bytes(int64_t n_local, int d, int dtype, int nq, int k, int nranks);
+int ragarc_sharded_topk(ragarc_comm_t* comm, const void* corpus_shard, int64_t n_local, int d, int dtype,
+                        const void* queries, int nq, int k, uint64_t id_base, float* out_scores,
+                        int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
 
 /* fp32-accurate search on the tensor cores ("bf16x3").  An fp32 vector v is stored as three bf16
  * planes v1+v2+v3 (v1 = bf16(v), v2 = bf16(v-v1), v3 = bf16(v-v1-v2); exact to 2^-24 relative), a

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RAGARC_LIB: load another build of the same library (e.g. one compiled with -DRAGARC_TC_STATS_BUILD)
 LIB_PATH = os.environ.get("RAGARC_LIB") or os.path.join(_HERE, "libragarc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu", "vocab.cu"]
+SOURCES = ["common.cu", "merge.cu", "dense_simt.cu", "dense_tc.cu", "bm25.cu", "misc.cu", "index.cu", "vocab.cu", "comm.cu"]
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
 METRIC_IP, METRIC_COSINE, METRIC_L2 = 0, 1, 2
@@ -34,8 +34,11 @@ EXPORTS = [
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_vocab_create", "ragarc_vocab_free", "ragarc_vocab_size",
     "ragarc_vocab_encode_split", "ragarc_vocab_encode_split0", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
     "ragarc_adjacent_cosine_distance", "ragarc_yes_no_score",
-    "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
+    "ragarc_host_alloc", "ragarc_host_free", "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
     "ragarc_index_remove", "ragarc_index_ntotal", "ragarc_index_dim", "ragarc_index_rows",
+    "ragarc_comm_nccl_version", "ragarc_comm_unique_id", "ragarc_comm_init_rank", "ragarc_comm_init_all",
+    "ragarc_comm_free", "ragarc_comm_rank", "ragarc_comm_nranks", "ragarc_sharded_topk_workspace_bytes",
+    "ragarc_sharded_topk",
     "ragarc_sharded_create", "ragarc_sharded_free", "ragarc_sharded_add", "ragarc_sharded_search",
     "ragarc_sharded_ntotal",
 ]
@@ -43,7 +46,7 @@ EXPORTS = [
 
 def nvcc_command(out: str = LIB_PATH):
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,550,128",
+            "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,550,128", "-ldl",
             *[os.path.join(CSRC, s) for s in SOURCES], "-o", out]
 
 
@@ -101,6 +104,8 @@ def _load():
         "ragarc_bm25_scores": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, P, P]),
         "ragarc_adjacent_cosine_distance": (c_int, [P, c_int, c_int64, c_int, P, P]),
         "ragarc_yes_no_score": (c_int, [P, c_int, c_int, c_int64, c_int, c_int, c_int, P, P]),
+        "ragarc_host_alloc": (c_int, [c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+        "ragarc_host_free": (c_int, [P]),
         "ragarc_index_create": (c_int, [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_void_p)]),
         "ragarc_index_free": (c_int, [P]),
         "ragarc_index_reserve": (c_int, [P, c_int64, P]),
@@ -110,6 +115,15 @@ def _load():
         "ragarc_index_ntotal": (c_int64, [P]),
         "ragarc_index_dim": (c_int, [P]),
         "ragarc_index_rows": (ctypes.c_void_p, [P]),
+        "ragarc_comm_nccl_version": (c_int, []),
+        "ragarc_comm_unique_id": (c_int, [P]),
+        "ragarc_comm_init_rank": (c_int, [P, c_int, c_int, ctypes.POINTER(ctypes.c_void_p)]),
+        "ragarc_comm_init_all": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_void_p)]),
+        "ragarc_comm_free": (c_int, [P]),
+        "ragarc_comm_rank": (c_int, [P]),
+        "ragarc_comm_nranks": (c_int, [P]),
+        "ragarc_sharded_topk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+        "ragarc_sharded_topk": (c_int, [P, P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, P, P, c_size_t, P]),
         "ragarc_sharded_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_void_p)]),
         "ragarc_sharded_free": (c_int, [P]),
         "ragarc_sharded_add": (c_int, [P, P, c_int64]),

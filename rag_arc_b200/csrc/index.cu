@@ -111,6 +111,18 @@ using namespace ragarc;
 
 extern "C" {
 
+int ragarc_host_alloc(size_t bytes, void** out_host) {
+  RA_REQUIRE(out_host != nullptr, "host_alloc: out is NULL");
+  *out_host = nullptr;
+  RA_CUDA(cudaHostAlloc(out_host, bytes > 0 ? bytes : 1, cudaHostAllocDefault));
+  return RAGARC_OK;
+}
+
+int ragarc_host_free(void* host) {
+  if (host) RA_CUDA(cudaFreeHost(host));
+  return RAGARC_OK;
+}
+
 int ragarc_index_create(int d, int dtype, int metric, ragarc_index_t** out) {
   RA_REQUIRE(out != nullptr, "index_create: out is NULL");
   *out = nullptr;

@@ -18,6 +18,36 @@ _DTYPES = {"float32": N.F32, "bfloat16": N.BF16, "float16": N.F16}
 _METRICS = {"ip": N.METRIC_IP, "cosine": N.METRIC_COSINE, "l2": N.METRIC_L2}
 
 
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked memory from ``ragarc_host_alloc`` (freed with the array): queries
+    and results handed to ``NativeFlatIndex.search(..., out=)`` in such arrays travel by direct DMA."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    N.check(N.lib.ragarc_host_alloc(nbytes, ctypes.byref(p)), "host_alloc")
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = _Pinned(p, buf)
+    arr_base = arr
+    import weakref
+    weakref.finalize(arr_base, _PINNED.pop, id(buf), None)
+    return arr
+
+
+class _Pinned:
+    def __init__(self, p, buf):
+        self.p, self.buf = p, buf
+
+    def __del__(self):
+        try:
+            N.lib.ragarc_host_free(self.p)
+        except Exception:
+            pass
+
+
+_PINNED: dict = {}
+
+
 class NativeFlatIndex:
     def __init__(self, d: int, dtype: str = "float32", metric: str = "cosine"):
         if dtype not in _DTYPES:
@@ -44,15 +74,20 @@ class NativeFlatIndex:
             raise ValueError(f"expected [n,{self.d}] float32 rows")
         N.check(N.lib.ragarc_index_add(self._h, x.ctypes.data, x.shape[0], 1, None), "index_add")
 
-    def search(self, q: np.ndarray, k: int):
+    def search(self, q: np.ndarray, k: int, out=None):
         """q: float32 [nq, d] host array -> (D float32 [nq,k] descending, I int64 [nq,k], -1 padded):
         the return contract of ``faiss.IndexFlatIP.search`` (metric "l2": squared distances ascending,
         that of ``faiss.IndexFlatL2.search``)."""
         q = np.ascontiguousarray(q, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.d:
             raise ValueError(f"expected [nq,{self.d}] float32 queries")
-        D = np.empty((q.shape[0], k), np.float32)
-        I = np.empty((q.shape[0], k), np.int64)
+        if out is not None:
+            D, I = out
+            if D.shape != (q.shape[0], k) or I.shape != D.shape or D.dtype != np.float32 or I.dtype != np.int64:
+                raise ValueError("out must be (float32 [nq,k], int64 [nq,k])")
+        else:
+            D = np.empty((q.shape[0], k), np.float32)
+            I = np.empty((q.shape[0], k), np.int64)
         N.check(N.lib.ragarc_index_search(self._h, q.ctypes.data, q.shape[0], int(k), D.ctypes.data,
                                           I.ctypes.data, 1, None), "index_search")
         return D, I
@@ -103,7 +138,7 @@ class NativeShardedIndex:
             raise ValueError(f"expected [n,{self.d}] float32 rows")
         N.check(N.lib.ragarc_sharded_add(self._h, x.ctypes.data, x.shape[0]), "sharded_add")
 
-    def search(self, q: np.ndarray, k: int):
+    def search(self, q: np.ndarray, k: int, out=None):
         q = np.ascontiguousarray(q, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.d:
             raise ValueError(f"expected [nq,{self.d}] float32 queries")

@@ -209,3 +209,40 @@ def test_async_wrappers_and_batch_defaults_of_the_plugin_bases():
     assert Document.from_dict(d.to_dict()) == d and Document("x").metadata == {} and Document("x").id is None
     with __import__("pytest").raises(TypeError):
         BaseRetriever()                                        # abstract
+
+
+def test_native_query_encoding_equals_python_split_and_lookup():
+    """ragarc_vocab_encode_split[0]: the batch tokenise + lookup + pack behind the C ABI must give exactly
+    what the reference's per-query Python does - ``query.split()`` (every str.isspace() character, UTF-8
+    multi-byte ones included) and a dictionary lookup per token (-1 = out of vocabulary) - for empty
+    queries, long queries (staging row regrown), repeated tokens, texts containing NUL, and random text."""
+    import random
+    import torch
+    from rag_arc_b200.core.retrieval.bm25_index import Bm25Index
+    spaces = [" ", "\t", "\n", "\x0b", "\x0c", "\r", "\x1c", "\x1d", "\x1e", "\x1f", "\x85", "\xa0", "\u1680", "\u2000",
+              "\u2005", "\u200a", "\u2028", "\u2029", "\u202f", "\u205f", "\u3000"]
+    assert all(c.isspace() for c in spaces)
+    non_spaces = ["\u200b", "\u180e", "\ufeff", "\x00", "\x7f", "\xad"]          # look-alikes that str.split() keeps
+    assert not any(c.isspace() for c in non_spaces)
+    words = ["alpha", "beta", "gamma", "\u00fcn\u00ef", "\u65e5\u672c\u8a9e", "x", "a\u200bb", "\ufeffbom", "t1", "t22"]
+    idx = Bm25Index.from_token_lists([words[:5], words[5:]], device=None)
+    idx.device = torch.device("cpu")
+    rnd = random.Random(7)
+    texts = ["", " ", "alpha", "alpha  beta\tgamma zzz", "x " * 70, "a\u200bb \ufeffbom", "alpha\x00beta x"]
+    for _ in range(300):
+        parts = []
+        for _ in range(rnd.randint(0, 12)):
+            parts.append(rnd.choice(words + ["oov", "\u00e9"]))
+            parts.append("".join(rnd.choice(spaces + non_spaces[:2]) for _ in range(rnd.randint(1, 3))))
+        texts.append("".join(parts))
+    for batch in (texts, texts[:6], texts[6:7], []):
+        qt, ql = idx.encode_texts(batch)
+        want = [[idx.vocab.get(t, -1) for t in s.split()] for s in batch]
+        assert ql.tolist() == [len(w) for w in want]
+        for i, row in enumerate(want):
+            assert qt[i, :len(row)].tolist() == row, (batch[i], qt[i].tolist(), row)
+            assert bool((qt[i, len(row):] == -1).all())
+        if batch:
+            qt2, ql2 = idx.encode_queries([s.split() for s in batch])
+            w = min(qt.shape[1], qt2.shape[1])
+            assert torch.equal(ql, ql2) and torch.equal(qt[:, :w], qt2[:, :w])
