@@ -292,6 +292,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (CG == 1) __syncthreads(); else cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: once every CTA of this grid is resident and has got here, a kernel
+  // launched behind it with programmatic stream serialisation may start.  That is how the left-over
+  // pairs' launch is ordered AFTER the placement of the multicast clusters (if its CTAs were placed
+  // first they could sit on SMs a 4-CTA cluster needs, and those clusters would only start when the
+  // left-over launch is done: measured +0.7 ms per search whenever the stream was busy at launch time).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int64_t items = (int64_t)MBq * p.S;       // cluster work items: (query-block group, slice)
 
@@ -624,7 +630,8 @@ static int max_clusters() {
 }
 
 template <int MODE, int CG, int CL>
-static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, cudaStream_t stream) {
+static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params& p, cudaStream_t stream,
+                      bool programmatic = false) {
   using C = Cfg<CG>;
   RA_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE, CG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   RA_REQUIRE(p.MB % CL == 0, "dense tcgen05: query blocks not divisible by the cluster's pair count");
@@ -637,13 +644,18 @@ static int launch_one(const CUtensorMap& mq, const CUtensorMap& mx, const Params
   cfg.blockDim = dim3(64 + 128 * (p.sets > 1 ? 2 : 1));
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG_;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (programmatic) {      // may start as soon as the previous kernel in the stream has issued launch_dependents everywhere
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   RA_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<MODE, CG, CL>, mq, mx, p));
   count_launch();
   return RAGARC_OK;
@@ -787,6 +799,23 @@ int launch_dense_tc(const void* corpus, int64_t n, int d, int dtype, const void*
   // overlap the two launches (measured: they ran back to back).
   p.S = pl.S - pl.S_tail;
   p.tiles = pl.tiles_main;
+  static const char* envpdl = getenv("RAGARC_TC_PDL");       // 0: left-over pairs on a side stream (fork/join events)
+  const bool pdl = !(envpdl && envpdl[0] == '0');
+  if (pdl && pl.S_tail > 0) {
+    // both launches in the caller's stream: the left-over pairs as a programmatic dependent of the clusters
+    rc = cl == 4 ? launch_one<MODE_TOPK, 2, 4>(mq, mx, p, stream) : launch_one<MODE_TOPK, 2, 2>(mq, mx, p, stream);
+    if (rc) return rc;
+    CUtensorMap mxt;
+    rc = make_map(&mxt, corpus, n, d, dtype, BN / cg);
+    if (rc) return rc;
+    Params pt = p;
+    pt.S = pl.S_tail;
+    pt.tiles = pl.tiles - pl.tiles_main;
+    pt.tile_base = pl.tiles_main;
+    pt.slice_base = pl.S - pl.S_tail;
+    pt.pub_publish = 0;                          // the left-over pairs read the rungs but publish none
+    return launch_one<MODE_TOPK, 2, 1>(mq, mxt, pt, stream, true);
+  }
   Side* side = nullptr;
   std::unique_lock<std::mutex> side_lock;          // the fork/join sequence on the shared side stream is atomic
   if (pl.S_tail > 0) {

@@ -5,6 +5,9 @@
 // own workspace and staging buffers, and accepts fp32 inputs and outputs either as device pointers
 // or as plain HOST buffers - a host that is not PyTorch (or not Python) needs nothing else.
 // All arithmetic is the stateless entry points' (ragarc_normalize_cast, ragarc_dense_topk).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -242,10 +245,15 @@ int ragarc_index_search(ragarc_index_t* ix, const float* queries, int nq, int k,
   float* d_scores = buffers_on_host ? (float*)(sg + q32_bytes + qs_bytes) : out_scores;
   int64_t* d_ids = buffers_on_host ? (int64_t*)(sg + q32_bytes + qs_bytes + os_bytes) : out_ids;
   const float* q_src = queries;
+  static const bool trace = getenv("RAGARC_INDEX_TRACE") != nullptr;      // experiments: per-phase wall clock on stderr
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_a = 0, t_b = 0, t_c = 0, t_d = 0;
+  if (trace) { cudaStreamSynchronize(st); t_a = now(); }
   if (buffers_on_host) {
     RA_CUDA(cudaMemcpyAsync(q32, queries, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
     q_src = q32;
   }
+  if (trace) { cudaStreamSynchronize(st); t_b = now(); }
   // faiss.normalize_L2 on the query when the metric is cosine (VectorStore_Faiss.py:259), then the
   // cast to the storage dtype; for fp32 storage without normalisation the queries are used in place
   const void* q_use = q_src;
@@ -266,11 +274,15 @@ int ragarc_index_search(ragarc_index_t* ix, const float* queries, int nq, int k,
     rc = ragarc_l2_distances(d_scores, qs, ix->dtype, nq, k, ix->d, stream);
     if (rc) return rc;
   }
+  if (trace) { t_c = now(); cudaStreamSynchronize(st); t_d = now(); }
   if (buffers_on_host) {
     RA_CUDA(cudaMemcpyAsync(out_scores, d_scores, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     RA_CUDA(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
     RA_CUDA(cudaStreamSynchronize(st));
   }
+  if (trace)
+    fprintf(stderr, "[index_search] h2d %.3f ms, enqueue kernels %.3f ms, kernels done +%.3f ms, d2h %.3f ms\n",
+            t_b - t_a, t_c - t_b, t_d - t_c, now() - t_d);
   return order_end(ix, st);
 }
 
