@@ -342,14 +342,17 @@ class Ctx:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
         return int(t.item()) == 1
 
-    def timed(self, fn, steps):
+    def timed(self, fn, steps, finish=None):
         """barrier + sync, `steps` calls bracketed by CUDA events on the current stream, barrier + sync;
-        device milliseconds, max over ranks."""
+        device milliseconds, max over ranks.  finish: makes the current stream wait for work the calls
+        put on streams of their own (the overlapped step), so that the closing event covers all of it."""
         e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1))
@@ -477,13 +480,23 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
         return sharded.search_owned(q_dev, k)
 
     step_device, graphed, out_s, out_i = step_eager, False, None, None
+    finish, overlapped = None, False
     if not ctx.args.no_graph:
         replay = None
         try:
-            if world == 1:
-                replay, out_s, out_i = store.index.capture_search(q_dev, k)
+            if ctx.args.no_overlap:
+                if world == 1:
+                    replay, out_s, out_i = store.index.capture_search(q_dev, k)
+                else:
+                    replay, out_s, out_i = sharded.capture(q_dev, k, owned=True)
             else:
-                replay, out_s, out_i = sharded.capture(q_dev, k, owned=True)
+                # two alternating slots: the selection / exchange of batch i runs under the scoring of batch i+1
+                if world == 1:
+                    replay, finish, outs = store.index.capture_search_overlapped(q_dev, k)
+                else:
+                    replay, finish, outs = sharded.capture_owned_overlapped(q_dev, k)
+                out_s, out_i = outs[0]
+                overlapped = True
         except Exception as exc:  # noqa: BLE001
             replay = None
             if rank == 0:
@@ -492,11 +505,14 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
         if ctx.all_ok(replay is not None):              # every rank replays, or none does
             step_device, graphed = replay, True
     # ---- warm-up + correctness of what is about to be timed -------------------------------------------
-    for _ in range(max(3, warmup)):
+    for _ in range(max(4, warmup + (warmup & 1))):       # even: the next call uses slot 0 again
         r = step_device()
+    if finish is not None and graphed:
+        finish()
     ctx.barrier()
     if not graphed:
         out_s, out_i = r
+        finish, overlapped = None, False
     verify = {"checked_queries": 0, "against": None}
     nv = min(verify_queries, q_hi - q_lo)
     if nv > 0:
@@ -539,7 +555,7 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
     ctx.barrier()                               # every rank (a rank-conditional barrier here would deadlock the run)
     if sampler is not None:
         sampler.mark_begin()
-    ms_total = ctx.timed(step_device, steps)
+    ms_total = ctx.timed(step_device, steps, finish)
     if sampler is not None:
         sampler.mark_end()
     launches = (N.launch_count() - launches0) if not graphed else launches_per_step * steps
@@ -547,6 +563,7 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
         "workload": wname, "rows": w["rows"], "dim": w["dim"], "batch": batch, "k": k, "dtype": w["dtype"],
         "rows_per_gpu": n_local, "value": steps * batch / (ms_total * 1e-3), "unit": "queries/s",
         "ms_per_step": ms_total / steps, "steps": steps, "cuda_graph": graphed, "gpu_launches": int(launches),
+        "overlapped_select": overlapped,
         "launches_per_step": int(launches_per_step),
         "parallelism": (f"row-shard x{world}; key exchange: {sharded.exchange_used}; every rank merges the "
                         f"{q_hi - q_lo} queries it owns" if world > 1 else "single GPU"),
@@ -560,7 +577,8 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
     if sustained_s > 0:
         n_sus = max(steps, int(sustained_s * 1e3 / max(res["ms_per_step"], 1e-3)) + 1)
         t_b = time.time()
-        ms_sus = ctx.timed(step_device, n_sus)
+        ms_sus = ctx.timed(step_device, n_sus + (n_sus & 1), finish)
+        n_sus += n_sus & 1
         t_e = time.time()
         sus = {"steps": n_sus, "seconds": ms_sus * 1e-3, "value": n_sus * batch / (ms_sus * 1e-3), "unit": "queries/s",
                "ms_per_step": ms_sus / n_sus}
@@ -956,6 +974,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if w["dtype"] == "bfloat16" else "f16", "data": "synthetic",
             "config": {"workload": args.workload, "rows": w["rows"], "dim": w["dim"], "batch": batch, "k": w["k"],
                        "rows_per_gpu": main["rows_per_gpu"], "parallelism": main["parallelism"], "cuda_graph": main["cuda_graph"],
+                       "overlapped_select": main["overlapped_select"],
                        "schedule": main["schedule"], "verified": main["verified"],
                        "l2_policy": f"inputs larger than L2 ({main['rows_per_gpu'] * w['dim'] * 2 / 1e9:.2f} GB corpus shard streamed every step)"},
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
@@ -975,6 +994,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one stream: no overlap of batch i's selection with batch i+1's scoring")
     ap.add_argument("--quick", action="store_true", help="headline only: no sustained run, no extra.c2/c4/c5 blocks")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)

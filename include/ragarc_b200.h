@@ -223,6 +223,31 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
                            int nq, int k, uint64_t id_base, uint64_t* out_keys, void* workspace,
                            size_t workspace_bytes, int path, int* path_used_host, void* stream);
 
+/* The general form: the two phases of a search as separate calls, so that a host can overlap the
+ * SELECTION of batch i (merge of the per-slice candidate lists: small, latency-bound, fits beside the
+ * persistent scoring CTAs on every SM) with the SCORING of batch i+1 on another stream.
+ *   phase RAGARC_PHASE_SCORE : scoring + fused per-slice selection into the workspace, no output
+ *   phase RAGARC_PHASE_SELECT: merge of what a SCORE call with the same (n, d, dtype, nq, k) left in the
+ *                              same workspace -> outputs; corpus / queries are not read (may be NULL)
+ *   phase RAGARC_PHASE_BOTH  : the two back to back (what ragarc_dense_topk does)
+ * Outputs (SELECT / BOTH): out_scores + out_ids, and/or out_keys (packed keys carrying id_base + row),
+ * or - inboxes != NULL - the query-owner push of ragarc_dense_topk_keys_push.  The caller orders a
+ * SELECT after its SCORE and keeps the workspace untouched in between (use one workspace per batch in
+ * flight). */
+enum { RAGARC_PHASE_BOTH = 0, RAGARC_PHASE_SCORE = 1, RAGARC_PHASE_SELECT = 2 };
+typedef struct ragarc_dense_opts {
+  int phase;
+  uint64_t id_base;
+  uint64_t* out_keys;             /* [nq,k] or NULL */
+  float* out_scores;              /* [nq,k] or NULL */
+  int64_t* out_ids;               /* [nq,k] or NULL */
+  uint64_t* const* inboxes;       /* DEVICE array of n_ranks inbox pointers, or NULL */
+  int n_ranks, rank, nq_per_rank, signal;
+} ragarc_dense_opts_t;
+int ragarc_dense_topk_ex(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq, int k,
+                         const ragarc_dense_opts_t* opts, void* workspace, size_t workspace_bytes, int path,
+                         int* path_used_host, void* stream);
+
 /* Same search for the query-owner exchange of the multi-GPU path (rag_arc_b200/sharded.py): the
  * sorted key row of query q is written straight into the inbox of the rank that owns the query,
  *   inboxes[q / nq_per_rank] + ((size_t)rank * nq_per_rank + q % nq_per_rank) * k,

@@ -27,7 +27,7 @@ EXPORTS = [
     "ragarc_abi_version", "ragarc_last_error", "ragarc_launch_count", "ragarc_profile_enable",
     "ragarc_profile_read", "ragarc_normalize_cast",
     "ragarc_dense_topk_workspace_bytes", "ragarc_dense_topk_plan", "ragarc_dense_topk", "ragarc_dense_topk_keys",
-    "ragarc_dense_topk_keys_push", "ragarc_merge_topk_inbox",
+    "ragarc_dense_topk_keys_push", "ragarc_merge_topk_inbox", "ragarc_dense_topk_ex",
     "ragarc_l2_aug_dim", "ragarc_l2_augment", "ragarc_l2_distances",
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
@@ -91,6 +91,8 @@ def _load():
                                            c_size_t, c_int, ctypes.POINTER(c_int), P]),
         "ragarc_dense_topk_keys_push": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, c_uint64, P, c_int,
                                                 c_int, c_int, c_int, P, c_size_t, c_int, ctypes.POINTER(c_int), P]),
+        "ragarc_dense_topk_ex": (c_int, [P, c_int64, c_int, c_int, P, c_int, c_int, P, P, c_size_t, c_int,
+                                         ctypes.POINTER(c_int), P]),
         "ragarc_merge_topk_inbox": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_double, P, P]),
         "ragarc_l2_aug_dim": (c_int, [c_int, c_int]),
         "ragarc_l2_augment": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
@@ -151,6 +153,16 @@ def _load():
 
 
 lib = _load()
+
+
+PHASE_BOTH, PHASE_SCORE, PHASE_SELECT = 0, 1, 2
+
+
+class DenseOpts(ctypes.Structure):
+    """``ragarc_dense_opts_t`` (include/ragarc_b200.h)."""
+    _fields_ = [("phase", c_int), ("id_base", c_uint64), ("out_keys", c_void_p), ("out_scores", c_void_p),
+                ("out_ids", c_void_p), ("inboxes", c_void_p), ("n_ranks", c_int), ("rank", c_int),
+                ("nq_per_rank", c_int), ("signal", c_int)]
 
 
 class RagArcError(RuntimeError):

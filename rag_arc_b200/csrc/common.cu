@@ -225,7 +225,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
                         int k, uint64_t id_base, uint64_t* out_keys, float* out_scores,
                         int64_t* out_ids, void* workspace, size_t workspace_bytes, int path,
                         int* path_used_host, cudaStream_t stream, int x3_d = 0,
-                        const MergePush* push = nullptr) {
+                        const MergePush* push = nullptr, int phase = RAGARC_PHASE_BOTH) {
   DensePlan pl;
   pl.x3_d = x3_d;
   int use = 0;
@@ -234,8 +234,9 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   if (rc) return rc;
   if (path_used_host) *path_used_host = use;
   if (nq == 0) return RAGARC_OK;
-  RA_REQUIRE(corpus || n == 0, "dense: null corpus");
-  RA_REQUIRE(queries, "dense: null queries");
+  const bool do_score = phase != RAGARC_PHASE_SELECT, do_select = phase != RAGARC_PHASE_SCORE;
+  RA_REQUIRE(!do_score || corpus || n == 0, "dense: null corpus");
+  RA_REQUIRE(!do_score || queries, "dense: null queries");
   RA_REQUIRE(workspace && workspace_bytes >= pl.total, "dense: workspace %zu < required %zu",
              workspace_bytes, pl.total);
   RA_REQUIRE(((uintptr_t)workspace & 255) == 0, "dense: workspace must be 256-byte aligned");
@@ -246,13 +247,19 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   // list lengths are written for every (item,row) by the scoring kernels, so only the shared
   // thresholds need a reset - and not even those when the seed pass overwrites all of them
   uint32_t* pub = (uint32_t*)(ws + pl.off_pub);
+  if (!do_score) {
+    // selection only: the candidate lists of an earlier RAGARC_PHASE_SCORE call with the same shape are
+    // in the workspace (the caller orders the two calls; they may be on different streams)
+    return launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, (uint64_t*)(ws + pl.off_mscratch), out_keys,
+                              out_scores, out_ids, push, stream);
+  }
   if (use == RAGARC_DENSE_TCGEN05 && pl.pub_n > 0)
     RA_CUDA(cudaMemsetAsync(gthr, 0, pl.off_keys - pl.off_gthr, stream));   // thresholds + published rungs
   else if (!(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0 && n > 0))
     RA_CUDA(cudaMemsetAsync(gthr, 0, (size_t)nq * 4, stream));
   if (n == 0) RA_CUDA(cudaMemsetAsync(counts, 0, pl.off_gthr - pl.off_counts, stream));
   ProfRec pr{};
-  const bool prof = g_prof_on.load() != 0;
+  const bool prof = g_prof_on.load() != 0 && do_select;
   if (prof) {
     RA_CUDA(cudaEventCreate(&pr.e0)); RA_CUDA(cudaEventCreate(&pr.e1)); RA_CUDA(cudaEventCreate(&pr.e2));
     RA_CUDA(cudaEventCreate(&pr.es));
@@ -271,6 +278,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
     RA_CUDA(cudaEventRecord(pr.es, stream));
   }
   if (prof) RA_CUDA(cudaEventRecord(pr.e1, stream));
+  if (!do_select) return RAGARC_OK;
   rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, (uint64_t*)(ws + pl.off_mscratch), out_keys,
                           out_scores, out_ids, push, stream);
   if (rc) return rc;
@@ -377,6 +385,29 @@ int ragarc_dense_topk_keys(const void* corpus, int64_t n, int d, int dtype, cons
   RA_REQUIRE(id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_keys: global ids must fit 32 bits");
   return dense_common(corpus, n, d, dtype, queries, nq, k, id_base, out_keys, nullptr, nullptr,
                       workspace, workspace_bytes, path, path_used_host, (cudaStream_t)stream);
+}
+
+int ragarc_dense_topk_ex(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq, int k,
+                         const ragarc_dense_opts_t* opts, void* workspace, size_t workspace_bytes, int path,
+                         int* path_used_host, void* stream) {
+  RA_REQUIRE(opts != nullptr, "dense_topk_ex: null options");
+  RA_REQUIRE(opts->phase == RAGARC_PHASE_BOTH || opts->phase == RAGARC_PHASE_SCORE || opts->phase == RAGARC_PHASE_SELECT,
+             "dense_topk_ex: bad phase %d", opts->phase);
+  const bool wants_out = opts->phase != RAGARC_PHASE_SCORE;
+  MergePush mp{nullptr, 0, 1, 0};
+  const MergePush* push = nullptr;
+  if (wants_out && opts->inboxes) {
+    RA_REQUIRE(opts->n_ranks > 0 && opts->rank >= 0 && opts->rank < opts->n_ranks && opts->nq_per_rank > 0 &&
+               (int64_t)opts->nq_per_rank * opts->n_ranks >= nq, "dense_topk_ex: bad query-owner partition");
+    mp = MergePush{opts->inboxes, opts->rank, opts->nq_per_rank, opts->signal ? opts->n_ranks : 0};
+    push = &mp;
+  } else if (wants_out) {
+    RA_REQUIRE(opts->out_keys || (opts->out_scores && opts->out_ids), "dense_topk_ex: no output given");
+  }
+  RA_REQUIRE(opts->id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_ex: global ids must fit 32 bits");
+  return dense_common(corpus, n, d, dtype, queries, nq, k, opts->id_base, push ? nullptr : opts->out_keys,
+                      push ? nullptr : opts->out_scores, push ? nullptr : opts->out_ids, workspace, workspace_bytes,
+                      path, path_used_host, (cudaStream_t)stream, 0, push, opts->phase);
 }
 
 int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,

@@ -97,16 +97,25 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
-// Bounded spin: a protocol bug traps (error returned to the host) instead of hanging the GPU.
+// Spin on an mbarrier phase.  The bound is wall-clock time, not a spin count: a stall of more than
+// ~20 s (checked every 2^16 polls against %globaltimer) traps, so that a protocol bug surfaces as an
+// error on the host instead of a hung GPU, while a debugger stop, an MPS time slice or a preemption -
+// which can hold a CTA for far longer than any spin count allows - do not kill the context.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t_first = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (spin > (1u << 26)) __trap();
+    if ((spin & 0xFFFFu) == 0xFFFFu) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_first == 0) t_first = now;
+      else if (now - t_first > 20000000000ull) __trap();
+    }
   }
 }
 // TMA tile load.  CG=2: the completion bytes are signalled on the LEADER CTA's barrier (the

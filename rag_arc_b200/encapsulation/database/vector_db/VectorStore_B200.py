@@ -180,6 +180,82 @@ class FlatIndexB200:
 
         return replay, scores, rows
 
+    def score_phase(self, q_prepared: torch.Tensor, k: int) -> None:
+        """Phase 1 of ``search_device``: scoring + per-slice selection into the active workspace."""
+        ops.dense_topk_phase(ops.N.PHASE_SCORE, self.aug if self.l2 else self.rows, q_prepared, q_prepared.shape[0], k,
+                             n_rows=self.ntotal)
+
+    def select_phase(self, q_prepared: torch.Tensor, k: int, out=None):
+        """Phase 2: merge of the candidate lists a ``score_phase`` call left in the same workspace."""
+        nq = q_prepared.shape[0]
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.float32, device=self.device),
+                   torch.empty((nq, k), dtype=torch.int64, device=self.device))
+        ops.dense_topk_phase(ops.N.PHASE_SELECT, self.aug if self.l2 else self.rows, None, nq, k, n_rows=self.ntotal, out=out)
+        if self.l2:
+            ops.l2_distances(out[0], q_prepared, self.d)
+        return out
+
+    def capture_search_overlapped(self, queries: torch.Tensor, k: int):
+        """Throughput form of ``capture_search`` for back-to-back batches: two alternating slots, the
+        scoring of call i+1 (its own high-priority stream) overlaps the selection / merge of call i (a
+        second stream) - the merge kernel's small CTAs fit beside the persistent scoring CTAs on every
+        SM, so its ~35 us disappear from the step.  Returns ``(replay, finish, outs)``: ``replay()``
+        enqueues one search of the (fixed) ``queries`` buffer, ``finish()`` makes the current stream
+        wait for everything enqueued so far, ``outs[j]`` = ``(scores, rows)`` of the calls with parity
+        j.  Every call still does all of its work; only the order in which the GPU runs it changes."""
+        if self.x3:
+            raise ValueError("the overlapped form is offered for bf16 / fp16 / fp32-FMA stores")
+        dev = self.device
+        torch.cuda.synchronize(dev)
+        s_score = torch.cuda.Stream(dev, priority=-1)
+        s_sel = torch.cuda.Stream(dev, priority=0)
+        cur = torch.cuda.current_stream(dev)
+        slots = []
+        for _ in range(2):
+            scope = ops.WorkspaceScope()
+            out = (torch.empty((queries.shape[0], k), dtype=torch.float32, device=dev),
+                   torch.empty((queries.shape[0], k), dtype=torch.int64, device=dev))
+            s_score.wait_stream(cur)
+            with scope, torch.cuda.stream(s_score):
+                self.score_phase(queries, k)               # warm-up: the scope's workspace exists now
+                s_score.synchronize()
+                g_score = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_score, stream=s_score):
+                    self.score_phase(queries, k)
+            s_sel.wait_stream(s_score)
+            with scope, torch.cuda.stream(s_sel):
+                self.select_phase(queries, k, out)
+                s_sel.synchronize()
+                g_sel = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_sel, stream=s_sel):
+                    self.select_phase(queries, k, out)
+            slots.append({"scope": scope, "out": out, "g_score": g_score, "g_sel": g_sel,
+                          "scored": torch.cuda.Event(), "selected": torch.cuda.Event()})
+        torch.cuda.synchronize(dev)
+        state = {"i": 0}
+
+        def replay():
+            sl = slots[state["i"] & 1]
+            if state["i"] < 2:
+                s_score.wait_stream(torch.cuda.current_stream(dev))        # inputs written on the caller's stream
+            state["i"] += 1
+            s_score.wait_event(sl["selected"])             # the slot's lists have been merged (two calls ago)
+            with torch.cuda.stream(s_score):
+                sl["g_score"].replay()
+                sl["scored"].record(s_score)
+            s_sel.wait_event(sl["scored"])
+            with torch.cuda.stream(s_sel):
+                sl["g_sel"].replay()
+                sl["selected"].record(s_sel)
+            return sl["out"]
+
+        def finish():
+            c = torch.cuda.current_stream(dev)
+            c.wait_stream(s_score); c.wait_stream(s_sel)
+
+        return replay, finish, [sl["out"] for sl in slots]
+
     def search(self, q, k: int):
         """faiss-style: numpy in, ``(D float32 [nq,k], I int64 [nq,k])`` numpy out."""
         D, I = self.search_device(self.prepare_queries(q), k)

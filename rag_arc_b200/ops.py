@@ -175,6 +175,37 @@ def dense_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, n_rows: O
     return scores, ids
 
 
+def dense_topk_phase(phase: int, corpus: torch.Tensor, queries: Optional[torch.Tensor], nq: int, k: int, *,
+                     n_rows: Optional[int] = None, id_base: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                     out_keys: Optional[torch.Tensor] = None, inbox_table: Optional[torch.Tensor] = None, rank: int = 0,
+                     nq_per_rank: int = 0, signal: bool = False, path: int = N.DENSE_AUTO):
+    """One phase of a search (``ragarc_dense_topk_ex``): ``N.PHASE_SCORE`` fills the candidate lists in
+    the active workspace, ``N.PHASE_SELECT`` merges them into ``out`` = (scores, ids) / ``out_keys`` /
+    the owners' inboxes.  Both calls must see the SAME workspace: run them inside one
+    ``WorkspaceScope`` (they may be on different streams; the caller orders them with events)."""
+    _cuda(corpus, "corpus")
+    n = corpus.shape[0] if n_rows is None else int(n_rows)
+    d = corpus.shape[1]
+    dev = corpus.device
+    code = dtype_code(corpus.dtype)
+    ws = _workspace(dev, int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, code, nq, k)), "dense")
+    o = N.DenseOpts()
+    o.phase, o.id_base = int(phase), int(id_base)
+    if phase != N.PHASE_SCORE:
+        if inbox_table is not None:
+            o.inboxes, o.n_ranks, o.rank, o.nq_per_rank, o.signal = (inbox_table.data_ptr(), inbox_table.numel(), int(rank),
+                                                                      int(nq_per_rank), int(bool(signal)))
+        else:
+            if out is not None:
+                o.out_scores, o.out_ids = out[0].data_ptr(), out[1].data_ptr()
+            if out_keys is not None:
+                o.out_keys = out_keys.data_ptr()
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_dense_topk_ex(corpus.data_ptr(), n, d, code, queries.data_ptr() if queries is not None else None,
+                                           nq, k, ctypes.byref(o), ws.data_ptr(), ws.numel(), path, None, _stream_ptr(dev)),
+                "dense_topk_ex")
+
+
 def normalize_split3(src: torch.Tensor, normalize: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [n,d] -> three bf16 planes [n,3d] (v = v1+v2+v3 to 2^-24), optionally L2-normalised first."""
     _cuda(src, "src")

@@ -106,6 +106,11 @@ class _OwnerExchange:
         slot = self.step & 1
         self.step += 1
         push(self.tables[slot], self.signalled)      # this rank's key rows -> the owners' inboxes
+        return self.merge_slot(slot, k_out)
+
+    def merge_slot(self, slot: int, k_out: int):
+        """Owner half for inbox ``slot``: wait until every rank's rows of this search have landed (arrival
+        counters inside the merge kernel, or one symmetric-memory barrier), merge the owned queries."""
         n_own = self.q_hi - self.q_lo
         if self.signalled:
             return ops.merge_topk_inbox(self.inbox[slot], self.world, self.nq_per, n_own, self.k, k_out, self.status)
@@ -195,6 +200,82 @@ class ShardedFlatIndex:
         return ox.push_and_merge(
             lambda table, signal: ops.dense_topk_keys_push(self.rows, queries, k, self.id_base, table, self.rank,
                                                            ox.nq_per, signal=signal, n_rows=self.n_local), k)
+
+    def capture_owned_overlapped(self, queries: torch.Tensor, k: int):
+        """Throughput form of ``capture(owned=True)``: per exchange slot one graph with the scoring phase
+        (high-priority stream) and one with everything after it - merge of the local candidate lists
+        pushed into the owners' inboxes, the cross-rank ordering, the owner's merge - on a second
+        stream, so that the exchange of search i runs under the scoring of search i+1.  Returns
+        ``(replay, finish, outs)`` like ``FlatIndexB200.capture_search_overlapped``; every rank must
+        call ``replay`` the same number of times."""
+        nq = queries.shape[0]
+        dev = queries.device
+        self.search_owned(queries, k); self.search_owned(queries, k)      # rendezvous, both inbox slots used once
+        ox = self._owner.get((nq, k))
+        if ox is None:
+            raise RuntimeError("the query-owner exchange is not available (no peer memory): use capture(owned=True)")
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+        s_score = torch.cuda.Stream(dev, priority=-1)
+        s_sel = torch.cuda.Stream(dev, priority=0)
+        cur = torch.cuda.current_stream(dev)
+        N = ops.N
+        slots = []
+        for slot in range(2):
+            scope = ops.WorkspaceScope()
+
+            def score():
+                ops.dense_topk_phase(N.PHASE_SCORE, self.rows, queries, nq, k, n_rows=self.n_local)
+
+            def select(slot=slot):
+                ops.dense_topk_phase(N.PHASE_SELECT, self.rows, None, nq, k, n_rows=self.n_local, id_base=self.id_base,
+                                     inbox_table=ox.tables[slot], rank=self.rank, nq_per_rank=ox.nq_per, signal=ox.signalled)
+                return ox.merge_slot(slot, k)
+
+            s_score.wait_stream(cur)
+            with scope, torch.cuda.stream(s_score):
+                score()
+                s_score.synchronize()
+            s_sel.wait_stream(s_score)
+            with scope, torch.cuda.stream(s_sel):
+                select()                                   # eager once: every rank pushes + merges this slot
+                s_sel.synchronize()
+            dist.barrier(group=self.group)
+            with scope, torch.cuda.stream(s_score):
+                g_score = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_score, stream=s_score):
+                    score()
+            with scope, torch.cuda.stream(s_sel):
+                g_sel = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_sel, stream=s_sel):
+                    out = select()
+            slots.append({"scope": scope, "out": out, "g_score": g_score, "g_sel": g_sel,
+                          "scored": torch.cuda.Event(), "selected": torch.cuda.Event()})
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+        state = {"i": 0}
+
+        def replay():
+            sl = slots[state["i"] & 1]
+            if state["i"] < 2:
+                s_score.wait_stream(torch.cuda.current_stream(dev))
+            state["i"] += 1
+            s_score.wait_event(sl["selected"])
+            with torch.cuda.stream(s_score):
+                sl["g_score"].replay()
+                sl["scored"].record(s_score)
+            s_sel.wait_event(sl["scored"])
+            with torch.cuda.stream(s_sel):
+                sl["g_sel"].replay()
+                sl["selected"].record(s_sel)
+            return sl["out"]
+
+        def finish():
+            c = torch.cuda.current_stream(dev)
+            c.wait_stream(s_score); c.wait_stream(s_sel)
+
+        self.exchange_used = ("owner-push" if ox.signalled else "owner-push+barrier") + ", exchange overlapped with the next scoring"
+        return replay, finish, [sl["out"] for sl in slots]
 
     def capture(self, queries: torch.Tensor, k: int, owned: bool = False):
         """CUDA-graph the whole search (scoring, key exchange, merge) for a fixed query buffer:

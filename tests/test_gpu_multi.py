@@ -82,6 +82,13 @@ def _owner_worker(rank, world, port, signal, out):
         s, i = replay()
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(i, i_ref[qlo:qhi]) and torch.equal(s, s_ref[qlo:qhi]))
+    replay2, finish2, outs2 = idx.capture_owned_overlapped(q, k)               # exchange of call i under scoring of call i+1
+    for it in range(5):
+        replay2()
+    finish2(); torch.cuda.synchronize()
+    for s2, i2 in outs2:
+        ok = ok and bool(torch.equal(i2, i_ref[qlo:qhi]) and torch.equal(s2, s_ref[qlo:qhi]))
+    replay2(); finish2(); torch.cuda.synchronize()                              # leaves both ranks on an even call count
     prepare = lambda q32: ops.normalize_cast(q32, torch.bfloat16, True)
     pipe = sharded.ShardedSearchPipeline(idx, prepare, nq, d, k, owned=True)
     batches = [torch.randn((nq, d), generator=torch.Generator().manual_seed(100 + b)).pin_memory() for b in range(4)]

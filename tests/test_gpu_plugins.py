@@ -183,6 +183,37 @@ def test_search_pipeline_equals_synchronous_search(dev):
     assert torch.equal(r2, r) and torch.equal(s2, s)
 
 
+@pytest.mark.parametrize("metric,dtype", [("cosine", "bfloat16"), ("l2", "float16")])
+def test_overlapped_capture_equals_plain_search(dev, metric, dtype):
+    """capture_search_overlapped: scoring of call i+1 on one stream, selection of call i on another, two
+    alternating workspaces - every call must still return exactly what the one-stream search returns,
+    also when the query buffer is refilled between calls."""
+    rng = np.random.default_rng(3)
+    vecs = rng.standard_normal((150_000, 128)).astype(np.float32)
+    store = B200VectorStore.from_embeddings([str(i) for i in range(len(vecs))], vecs, metric=metric, dtype=dtype, device=dev)
+    ix = store.index
+    batches = [torch.from_numpy(rng.standard_normal((300, 128)).astype(np.float32)).to(dev) for _ in range(5)]
+    qbuf = ix.prepare_queries(batches[0]).clone()
+    replay, finish, outs = ix.capture_search_overlapped(qbuf, 20)
+    got = []
+    for b in batches:
+        finish(); torch.cuda.synchronize()                    # the buffer is about to be overwritten
+        qbuf.copy_(ix.prepare_queries(b))
+        s, r = replay()
+        finish(); torch.cuda.synchronize()
+        got.append((s.clone(), r.clone()))
+    for b, (s, r) in zip(batches, got):
+        ws, wr = ix.search_device(ix.prepare_queries(b), 20)
+        assert torch.equal(r, wr) and torch.equal(s, ws)
+    # back to back without waiting in between (same queries): both slots end up with the same answer
+    for _ in range(7):
+        replay()
+    finish(); torch.cuda.synchronize()
+    ws, wr = ix.search_device(qbuf, 20)
+    for s, r in outs:
+        assert torch.equal(r, wr) and torch.equal(s, ws)
+
+
 def test_float32x3_store_matches_fp32_golden(dev, tmp_path):
     """dtype="float32x3": fp32-accurate tensor-core search behind the same plugin; must reproduce the
     reference FaissVectorStore golden exactly like the fp32 SIMT store does (d=48 is not a multiple
