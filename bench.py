@@ -484,7 +484,7 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
     if not ctx.args.no_graph:
         replay = None
         try:
-            if ctx.args.no_overlap:
+            if not ctx.args.overlap:
                 if world == 1:
                     replay, out_s, out_i = store.index.capture_search(q_dev, k)
                 else:
@@ -994,7 +994,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="one stream: no overlap of batch i's selection with batch i+1's scoring")
+    ap.add_argument("--overlap", action="store_true",
+                    help="two alternating slots: selection / exchange of batch i on a second stream under the scoring of "
+                         "batch i+1 (measured: no faster than the one-stream step, profiles/r02_overlap_ab.txt)")
     ap.add_argument("--quick", action="store_true", help="headline only: no sustained run, no extra.c2/c4/c5 blocks")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)

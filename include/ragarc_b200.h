@@ -243,6 +243,8 @@ typedef struct ragarc_dense_opts {
   int64_t* out_ids;               /* [nq,k] or NULL */
   uint64_t* const* inboxes;       /* DEVICE array of n_ranks inbox pointers, or NULL */
   int n_ranks, rank, nq_per_rank, signal;
+  int workspace_clean;            /* SCORE only: a SELECT ran on this workspace since its last SCORE (SELECT resets
+                                     the thresholds behind its merge), so the scoring kernel needs no memset in front */
 } ragarc_dense_opts_t;
 int ragarc_dense_topk_ex(const void* corpus, int64_t n, int d, int dtype, const void* queries, int nq, int k,
                          const ragarc_dense_opts_t* opts, void* workspace, size_t workspace_bytes, int path,

@@ -162,7 +162,7 @@ class DenseOpts(ctypes.Structure):
     """``ragarc_dense_opts_t`` (include/ragarc_b200.h)."""
     _fields_ = [("phase", c_int), ("id_base", c_uint64), ("out_keys", c_void_p), ("out_scores", c_void_p),
                 ("out_ids", c_void_p), ("inboxes", c_void_p), ("n_ranks", c_int), ("rank", c_int),
-                ("nq_per_rank", c_int), ("signal", c_int)]
+                ("nq_per_rank", c_int), ("signal", c_int), ("workspace_clean", c_int)]
 
 
 class RagArcError(RuntimeError):

@@ -225,7 +225,7 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
                         int k, uint64_t id_base, uint64_t* out_keys, float* out_scores,
                         int64_t* out_ids, void* workspace, size_t workspace_bytes, int path,
                         int* path_used_host, cudaStream_t stream, int x3_d = 0,
-                        const MergePush* push = nullptr, int phase = RAGARC_PHASE_BOTH) {
+                        const MergePush* push = nullptr, int phase = RAGARC_PHASE_BOTH, bool ws_clean = false) {
   DensePlan pl;
   pl.x3_d = x3_d;
   int use = 0;
@@ -249,11 +249,18 @@ static int dense_common(const void* corpus, int64_t n, int d, int dtype, const v
   uint32_t* pub = (uint32_t*)(ws + pl.off_pub);
   if (!do_score) {
     // selection only: the candidate lists of an earlier RAGARC_PHASE_SCORE call with the same shape are
-    // in the workspace (the caller orders the two calls; they may be on different streams)
-    return launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, (uint64_t*)(ws + pl.off_mscratch), out_keys,
-                              out_scores, out_ids, push, stream);
+    // in the workspace (the caller orders the two calls; they may be on different streams).  The
+    // thresholds and published rungs are reset BEHIND the merge, so that the next SCORE on this
+    // workspace can start with its scoring kernel instead of a memset (workspace_clean).
+    rc = launch_merge_lists(lists, counts, pl, nq, k, id_base, gthr, (uint64_t*)(ws + pl.off_mscratch), out_keys,
+                            out_scores, out_ids, push, stream);
+    if (rc) return rc;
+    RA_CUDA(cudaMemsetAsync(gthr, 0, pl.off_keys - pl.off_gthr, stream));
+    return RAGARC_OK;
   }
-  if (use == RAGARC_DENSE_TCGEN05 && pl.pub_n > 0)
+  if (ws_clean && phase == RAGARC_PHASE_SCORE && !(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0)) {
+    // the caller vouches that a SELECT (which resets them) ran on this workspace since the last SCORE
+  } else if (use == RAGARC_DENSE_TCGEN05 && pl.pub_n > 0)
     RA_CUDA(cudaMemsetAsync(gthr, 0, pl.off_keys - pl.off_gthr, stream));   // thresholds + published rungs
   else if (!(use == RAGARC_DENSE_TCGEN05 && pl.seed_rows > 0 && n > 0))
     RA_CUDA(cudaMemsetAsync(gthr, 0, (size_t)nq * 4, stream));
@@ -407,7 +414,7 @@ int ragarc_dense_topk_ex(const void* corpus, int64_t n, int d, int dtype, const 
   RA_REQUIRE(opts->id_base + (uint64_t)n < 0xFFFFFFF0ull, "dense_topk_ex: global ids must fit 32 bits");
   return dense_common(corpus, n, d, dtype, queries, nq, k, opts->id_base, push ? nullptr : opts->out_keys,
                       push ? nullptr : opts->out_scores, push ? nullptr : opts->out_ids, workspace, workspace_bytes,
-                      path, path_used_host, (cudaStream_t)stream, 0, push, opts->phase);
+                      path, path_used_host, (cudaStream_t)stream, 0, push, opts->phase, opts->workspace_clean != 0);
 }
 
 int ragarc_dense_topk_keys_push(const void* corpus, int64_t n, int d, int dtype, const void* queries,

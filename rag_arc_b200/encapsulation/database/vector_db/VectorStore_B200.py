@@ -180,10 +180,10 @@ class FlatIndexB200:
 
         return replay, scores, rows
 
-    def score_phase(self, q_prepared: torch.Tensor, k: int) -> None:
+    def score_phase(self, q_prepared: torch.Tensor, k: int, workspace_clean: bool = False) -> None:
         """Phase 1 of ``search_device``: scoring + per-slice selection into the active workspace."""
         ops.dense_topk_phase(ops.N.PHASE_SCORE, self.aug if self.l2 else self.rows, q_prepared, q_prepared.shape[0], k,
-                             n_rows=self.ntotal)
+                             n_rows=self.ntotal, workspace_clean=workspace_clean)
 
     def select_phase(self, q_prepared: torch.Tensor, k: int, out=None):
         """Phase 2: merge of the candidate lists a ``score_phase`` call left in the same workspace."""
@@ -220,16 +220,18 @@ class FlatIndexB200:
             with scope, torch.cuda.stream(s_score):
                 self.score_phase(queries, k)               # warm-up: the scope's workspace exists now
                 s_score.synchronize()
-                g_score = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_score, stream=s_score):
-                    self.score_phase(queries, k)
             s_sel.wait_stream(s_score)
             with scope, torch.cuda.stream(s_sel):
-                self.select_phase(queries, k, out)
+                self.select_phase(queries, k, out)         # ... and leaves thresholds / rungs reset behind its merge
                 s_sel.synchronize()
                 g_sel = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_sel, stream=s_sel):
                     self.select_phase(queries, k, out)
+            with scope, torch.cuda.stream(s_score):
+                # the scoring graph is the scoring kernels only: every replay follows a select on the slot
+                g_score = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_score, stream=s_score):
+                    self.score_phase(queries, k, workspace_clean=True)
             slots.append({"scope": scope, "out": out, "g_score": g_score, "g_sel": g_sel,
                           "scored": torch.cuda.Event(), "selected": torch.cuda.Event()})
         torch.cuda.synchronize(dev)

@@ -178,7 +178,7 @@ def dense_topk(corpus: torch.Tensor, queries: torch.Tensor, k: int, *, n_rows: O
 def dense_topk_phase(phase: int, corpus: torch.Tensor, queries: Optional[torch.Tensor], nq: int, k: int, *,
                      n_rows: Optional[int] = None, id_base: int = 0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                      out_keys: Optional[torch.Tensor] = None, inbox_table: Optional[torch.Tensor] = None, rank: int = 0,
-                     nq_per_rank: int = 0, signal: bool = False, path: int = N.DENSE_AUTO):
+                     nq_per_rank: int = 0, signal: bool = False, workspace_clean: bool = False, path: int = N.DENSE_AUTO):
     """One phase of a search (``ragarc_dense_topk_ex``): ``N.PHASE_SCORE`` fills the candidate lists in
     the active workspace, ``N.PHASE_SELECT`` merges them into ``out`` = (scores, ids) / ``out_keys`` /
     the owners' inboxes.  Both calls must see the SAME workspace: run them inside one
@@ -191,6 +191,7 @@ def dense_topk_phase(phase: int, corpus: torch.Tensor, queries: Optional[torch.T
     ws = _workspace(dev, int(N.lib.ragarc_dense_topk_workspace_bytes(n, d, code, nq, k)), "dense")
     o = N.DenseOpts()
     o.phase, o.id_base = int(phase), int(id_base)
+    o.workspace_clean = int(bool(workspace_clean))
     if phase != N.PHASE_SCORE:
         if inbox_table is not None:
             o.inboxes, o.n_ranks, o.rank, o.nq_per_rank, o.signal = (inbox_table.data_ptr(), inbox_table.numel(), int(rank),

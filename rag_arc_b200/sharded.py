@@ -224,8 +224,8 @@ class ShardedFlatIndex:
         for slot in range(2):
             scope = ops.WorkspaceScope()
 
-            def score():
-                ops.dense_topk_phase(N.PHASE_SCORE, self.rows, queries, nq, k, n_rows=self.n_local)
+            def score(clean=False):
+                ops.dense_topk_phase(N.PHASE_SCORE, self.rows, queries, nq, k, n_rows=self.n_local, workspace_clean=clean)
 
             def select(slot=slot):
                 ops.dense_topk_phase(N.PHASE_SELECT, self.rows, None, nq, k, n_rows=self.n_local, id_base=self.id_base,
@@ -244,7 +244,7 @@ class ShardedFlatIndex:
             with scope, torch.cuda.stream(s_score):
                 g_score = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_score, stream=s_score):
-                    score()
+                    score(clean=True)                      # the eager select above left the thresholds reset
             with scope, torch.cuda.stream(s_sel):
                 g_sel = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_sel, stream=s_sel):
