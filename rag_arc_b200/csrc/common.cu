@@ -106,7 +106,9 @@ int plan_dense(int64_t n, int d, int dtype, int nq, int k, int path, DensePlan* 
     int64_t smax = merge_cap / k;
     if (smax > pl->tiles / 2) smax = pl->tiles / 2;
     static const char* envr = getenv("RAGARC_TC_RHO");      // per-pair speed of a cluster vs a plain pair
-    const double rho = envr ? atof(envr) : (cl == 2 ? 1.09 : 1.15);
+    // measured with the rung thresholds in place: clusters of two pairs are ~3 % faster per pair than plain
+    // pairs (1.09 with the seeding pass; profiles/r02_rungs_timeline.txt, A/B in profiles/r02_split_ab.txt)
+    const double rho = envr ? atof(envr) : (cl == 2 ? 1.03 : 1.15);
     for (int waves = 2; waves >= 1 && S == 0; --waves) {
       const int64_t sm = waves * clusters * cl / pl->MB, st = waves * spare / pl->MB;
       if (sm < 1 || sm + st > smax) continue;
