@@ -53,6 +53,14 @@ def _worker(rank, world, port, n, d, nq, k, out):
     from oracle import dense as odense
     D, I = odense.flat_ip_search(X, Q, k)
     ok = bool((ids.numpy() == I).all() and np.array_equal(scores.numpy(), D))
+    # query-owner form: without peer memory (CPU, gloo) it falls back to the all-gather + slice; the owned
+    # ranges of the ranks partition the batch and every rank holds exactly its slice of the global result
+    qlo, qhi = idx.owned_range(nq)
+    s_own, i_own = idx.search_owned(torch.from_numpy(Q), k)
+    ok = ok and bool((i_own.numpy() == I[qlo:qhi]).all() and np.array_equal(s_own.numpy(), D[qlo:qhi]))
+    bounds = [None] * world
+    dist.all_gather_object(bounds, (qlo, qhi))
+    ok = ok and bounds[0][0] == 0 and bounds[-1][1] == nq and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
