@@ -67,7 +67,18 @@ class MultiPathRetriever(BaseRetriever):
         key_last_row = np.full((len(self.retrievers), max(len(keys), 1)), -1, np.int64)
         for l, tab in enumerate(tabs):
             key_last_row[l, tab] = np.arange(len(tab))       # later rows overwrite earlier ones
-        self._canon_cache = (sig, keys, tables, key_last_row)
+        # the same table on the device (resolution of fused keys to (retriever, row) happens there) and the
+        # documents of every retriever as one object array (row -> Document by fancy indexing, plus a
+        # trailing None that row -1 selects)
+        key_last_row_dev = torch.from_numpy(key_last_row).to(device)
+        doc_arrays = []
+        for r in self.retrievers:
+            docs = r.row_documents()
+            arr = np.empty(len(docs) + 1, dtype=object)
+            arr[:len(docs)] = docs
+            arr[len(docs)] = None
+            doc_arrays.append(arr)
+        self._canon_cache = (sig, keys, tables, key_last_row, key_last_row_dev, doc_arrays)
         return keys, tables
 
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
@@ -96,22 +107,29 @@ class MultiPathRetriever(BaseRetriever):
             per_list.append(keys if keys is not None else torch.full((nq, kl), -1, dtype=torch.int32, device=device))
         ids = torch.stack(per_list, 0)
         fused_ids, _, counts = self.fusion_method.fuse_batch(ids, top_k)
-        # one device->host transfer for everything the document lookup needs
-        packed = torch.cat([fused_ids.reshape(-1), counts.reshape(-1), ids.reshape(-1)]).cpu().numpy()
-        fused_ids = packed[:nq * top_k].reshape(nq, top_k)
-        counts = packed[nq * top_k:nq * top_k + nq]
-        ids_h = packed[nq * top_k + nq:].reshape(L, nq, kl)
         # reference semantics: the Document returned for a content string is the LAST one seen
         # while walking the lists in retriever order (Fusion.py:61) - i.e. it comes from the last
         # retriever whose list holds the key; inside one retriever duplicate contents resolve to the
-        # last row carrying them
-        row_docs = [r.row_documents() for r in self.retrievers]
-        key_last_row = self._canon_cache[3]
-        present = (ids_h[:, :, None, :] == fused_ids[None, :, :, None]).any(axis=3)    # [L, nq, top_k]
-        last_l = (L - 1) - np.argmax(present[::-1], axis=0)                            # [nq, top_k]
-        rows = key_last_row[last_l, np.clip(fused_ids, 0, None)]                       # [nq, top_k]
-        ll, rr, cc = last_l.tolist(), rows.tolist(), counts.tolist()
-        return [[row_docs[l][r] if r >= 0 else None for l, r in zip(ll[q][:cc[q]], rr[q][:cc[q]])] for q in range(nq)]
+        # last row carrying them.  Resolved on the device; one small device->host transfer.
+        key_last_row_dev, doc_arrays = self._canon_cache[4], self._canon_cache[5]
+        present = (ids[:, :, None, :] == fused_ids[None, :, :, None]).any(dim=3)       # [L, nq, top_k]
+        last_l = (L - 1) - torch.argmax(present.flip(0).to(torch.uint8), dim=0)        # [nq, top_k]
+        rows = key_last_row_dev[last_l, fused_ids.clamp(min=0).long()]                 # [nq, top_k]
+        rows = torch.where(fused_ids >= 0, rows, torch.full_like(rows, -1))
+        packed = torch.cat([last_l.reshape(-1), rows.reshape(-1), counts.reshape(-1).long()]).cpu().numpy()
+        last_l = packed[:nq * top_k].reshape(nq, top_k)
+        rows = packed[nq * top_k:2 * nq * top_k].reshape(nq, top_k)
+        counts = packed[2 * nq * top_k:]
+        # row -> Document by fancy indexing into the per-retriever object arrays (row -1 -> None)
+        out = np.empty((nq, top_k), dtype=object)
+        for l, arr in enumerate(doc_arrays):
+            sel = last_l == l
+            if sel.any():
+                out[sel] = arr[rows[sel]]
+        full = out.tolist()
+        if int(counts.min(initial=top_k)) >= top_k:
+            return full
+        return [row[:c] for row, c in zip(full, counts.tolist())]
 
     # ---- management --------------------------------------------------------------------------------
     def add_retriever(self, retriever: BaseRetriever):

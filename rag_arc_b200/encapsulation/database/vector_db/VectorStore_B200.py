@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import os
 import pickle
+import threading
 import uuid
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
@@ -73,6 +74,7 @@ class FlatIndexB200:
         self.rows = torch.empty((0, self.d), dtype=dtype, device=self.device)
         # metric "l2" (faiss.IndexFlatL2): next to the plain rows, the augmented matrix [x | -|x|^2/2]
         # the inner-product kernels search (ragarc_l2_augment); results are squared distances, ascending
+        self._stage_lock = threading.Lock()
         self.l2 = bool(l2)
         self.d_aug = ops.l2_aug_dim(self.d, dtype) if l2 else self.d
         self.aug = torch.empty((0, self.d_aug), dtype=dtype, device=self.device) if l2 else None
@@ -132,11 +134,34 @@ class FlatIndexB200:
     def reset(self) -> None:
         self.ntotal = 0
 
+    def _to_device_f32(self, qt: torch.Tensor) -> torch.Tensor:
+        """Host fp32 queries -> device.  Pageable memory goes through a page-locked staging buffer owned
+        by the index (one CPU copy + an asynchronous DMA instead of the driver's synchronous bounce);
+        the buffer is only rewritten after the previous transfer out of it has completed."""
+        if qt.is_cuda or self.device.type != "cuda":
+            return qt.to(device=self.device, dtype=torch.float32).contiguous()
+        qt = qt.to(torch.float32).contiguous()
+        if qt.is_pinned():
+            return qt.to(self.device, non_blocking=True)
+        if qt.numel() * 4 < (64 << 10):                   # single queries: the driver's inline copy is as fast
+            return qt.to(self.device)
+        with self._stage_lock:                             # retrievers run from thread pools (base.py:82-96)
+            st = getattr(self, "_q_stage", None)
+            if st is None or st[0].numel() < qt.numel():
+                st = self._q_stage = (torch.empty((qt.numel(),), dtype=torch.float32).pin_memory(), torch.cuda.Event())
+            else:
+                st[1].synchronize()                        # the previous transfer out of the buffer is done
+            view = st[0][:qt.numel()].view(qt.shape)
+            view.copy_(qt)
+            dev = view.to(self.device, non_blocking=True)
+            st[1].record(torch.cuda.current_stream(self.device))
+        return dev
+
     def prepare_queries(self, q) -> torch.Tensor:
         qt = torch.as_tensor(q)
         if qt.dim() == 1:
             qt = qt[None, :]
-        qt = qt.to(device=self.device, dtype=torch.float32).contiguous()
+        qt = self._to_device_f32(qt)
         if self.x3:
             return ops.normalize_split3(qt, self.normalize)
         if self.l2:
