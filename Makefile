@@ -5,11 +5,16 @@ NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -X
 CSRC      := $(sort $(wildcard rag_arc_b200/csrc/*.cu))
 LIB       := rag_arc_b200/libragarc_b200.so
 
-.PHONY: lib ctest clean
+.PHONY: lib stats ctest clean
 lib: $(LIB)
 
 $(LIB): $(CSRC) rag_arc_b200/csrc/common.cuh include/ragarc_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared $(CSRC) -o $@ -ldl
+
+# the same library with the scoring kernel's experiment counters compiled in (benchmarks/tc_stats.py:
+# RAGARC_LIB=$(abspath rag_arc_b200/libragarc_b200_stats.so) RAGARC_TC_STATS=1 python benchmarks/tc_stats.py)
+stats: $(CSRC) rag_arc_b200/csrc/common.cuh include/ragarc_b200.h
+	$(NVCC) $(NVCCFLAGS) -DRAGARC_TC_STATS_BUILD -shared $(CSRC) -o rag_arc_b200/libragarc_b200_stats.so -ldl
 
 # tests/c/index_smoke.c: needs a B200 to pass; without one it exits 2 with RAGARC_ERR_CUDA
 ctest: $(LIB)
@@ -18,4 +23,4 @@ ctest: $(LIB)
 	tests/c/index_smoke
 
 clean:
-	rm -f $(LIB) tests/c/index_smoke
+	rm -f $(LIB) rag_arc_b200/libragarc_b200_stats.so tests/c/index_smoke

@@ -550,10 +550,16 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           uint32_t g = *(volatile uint32_t*)grow;
           g = g > st.ord_global ? g : st.ord_global;
           if (g > st.ord_local) {
+            // sixteen loads in flight per pass: one key at a time is a dependent L2 round trip each (the
+            // compiler may not hoist loads over the compacting stores) and cost ~50-100 us per item
             int w = 0;
-            for (int i = 0; i < st.cnt; ++i) {
-              const uint64_t key = st.list[i];
-              if (uint32_t(key >> 32) >= g) st.list[w++] = key;
+            for (int i = 0; i < st.cnt; i += 16) {
+              uint64_t kk[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) kk[u] = (i + u < st.cnt) ? st.list[i + u] : 0ull;
+#pragma unroll
+              for (int u = 0; u < 16; ++u)
+                if (uint32_t(kk[u] >> 32) >= g && kk[u] != 0ull) st.list[w++] = kk[u];
             }
             st.cnt = w;
           }
