@@ -573,6 +573,17 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
     }
     res["step_roofline_frac"] = (res["roofline"]["tensor_floor_ms"] if res["roofline"]["bound"] == "tensor"
                                  else res["roofline"]["hbm_floor_ms"]) / res["ms_per_step"]
+    # ---- the same-shape GEMM by cuBLAS (scores only, no selection), back to back in the same clock state:
+    # the live yardstick for the step on THIS box (a power-capped B200 runs below the burst peak)
+    if full and world == 1 and res["roofline"]["bound"] == "tensor" and batch * n_local * 2 <= (8 << 30):
+        xt = x[:n_local].T
+        for _ in range(3):
+            sc_ = torch.matmul(q_dev, xt)
+        gemm_ms = ctx.timed(lambda: torch.matmul(q_dev, xt), steps, None) / steps
+        del sc_
+        torch.cuda.empty_cache()
+        res["roofline"]["cublas_gemm_same_shape_ms"] = gemm_ms
+        res["roofline"]["step_vs_cublas_gemm"] = gemm_ms / res["ms_per_step"]
     # ---- sustained: >= sustained_s seconds back to back, clocks sampled throughout -------------------------
     if sustained_s > 0:
         n_sus = max(steps, int(sustained_s * 1e3 / max(res["ms_per_step"], 1e-3)) + 1)
