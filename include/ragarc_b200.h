@@ -357,6 +357,20 @@ int ragarc_bm25_merge_topk(const double* scores, const int64_t* ids, int n_lists
 int ragarc_rrf_fuse(const int32_t* ids, int n_lists, int nq, int kl, double rrf_k, int top_k,
                     int32_t* out_ids, double* out_scores, int32_t* out_count, void* stream);
 
+/* The hybrid merge of MultiPathRetriever._get_relevant_documents (core/retrieval/mutipath.py:57-93) in one
+ * launch, on the retrievers' own result ROWS: list l arrives as rows[l] = device int64 [nq, kl_each[l]]
+ * (corpus rows of retriever l, -1 = padding; a NULL pointer = that retriever returned nothing), the
+ * content key of a row is row_to_key[l][row] (device int32, one entry per corpus row of retriever l; equal
+ * contents share a key across retrievers, which is how the reference de-duplicates: Fusion.py:57-61).
+ * Fusion as ragarc_rrf_fuse with kl columns per list (shorter lists are padded).  Besides the fused keys,
+ * scores and counts, every fused entry gets the Document the reference returns for it - the one at the LAST
+ * position holding the key, because document_map[content] is overwritten while the lists are walked in
+ * order (Fusion.py:61): out_list[nq, top_k] = its list, out_row[nq, top_k] = its row in that list's corpus,
+ * both -1 past out_count.  rows / kl_each / row_to_key are HOST arrays of n_lists entries (<= 8). */
+int ragarc_rrf_fuse_rows(const int64_t* const* rows, const int* kl_each, const int32_t* const* row_to_key,
+                         int n_lists, int nq, int kl, double rrf_k, int top_k, int32_t* out_ids, double* out_scores,
+                         int32_t* out_count, int32_t* out_list, int64_t* out_row, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Pool + L2-normalise encoder outputs.   Replaces the Pooling/Normalize tail of
  *   SentenceTransformer.encode behind core/file_management/embeddings/huggingface.py:122-126.

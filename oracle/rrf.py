@@ -18,7 +18,7 @@ from __future__ import annotations
 
 from typing import List, Sequence, Tuple
 
-__all__ = ["rrf_fuse_ids"]
+__all__ = ["rrf_fuse_ids", "rrf_fuse_rows"]
 
 
 def rrf_fuse_ids(lists: Sequence[Sequence[int]], top_k: int, k: float = 60.0
@@ -33,3 +33,22 @@ def rrf_fuse_ids(lists: Sequence[Sequence[int]], top_k: int, k: float = 60.0
             acc[key] = acc.get(key, 0.0) + 1.0 / (k + (pos + 1))
     order = sorted(acc.items(), key=lambda kv: kv[1], reverse=True)[:top_k]
     return [kv[0] for kv in order], [kv[1] for kv in order]
+
+
+def rrf_fuse_rows(rows: Sequence[Sequence[int]], row_contents: Sequence[Sequence[str]], top_k: int, k: float = 60.0
+                  ) -> Tuple[List[Tuple[int, int]], List[float]]:
+    """The hybrid merge as the reference performs it on Documents (``mutipath.py:57-93`` feeding
+    ``Fusion.py:45-76``), stated on corpus rows: ``rows[l]`` is retriever l's ranked list of rows into its own
+    corpus (negative = padding), ``row_contents[l][row]`` the content string of that row.  Returns, per fused
+    entry, ``(list, row)`` of the Document ``document_map`` holds when the walk is over - the last (list,
+    position) whose content equals the key (``Fusion.py:61``) - and the fused scores."""
+    acc, last = {}, {}
+    for l, ranked in enumerate(rows):
+        for pos, row in enumerate(ranked):
+            if row < 0:
+                continue
+            content = row_contents[l][row]
+            acc[content] = acc.get(content, 0.0) + 1.0 / (k + (pos + 1))
+            last[content] = (l, row)
+    order = sorted(acc.items(), key=lambda kv: kv[1], reverse=True)[:top_k]
+    return [last[c] for c, _ in order], [sc for _, sc in order]

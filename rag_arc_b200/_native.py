@@ -32,7 +32,7 @@ EXPORTS = [
     "ragarc_normalize_split3", "ragarc_dense_topk_x3_workspace_bytes", "ragarc_dense_topk_x3",
     "ragarc_merge_topk_keys", "ragarc_merge_topk_keys_p2p", "ragarc_bm25_workspace_bytes", "ragarc_bm25_scores",
     "ragarc_bm25_topk", "ragarc_bm25_merge_topk", "ragarc_vocab_create", "ragarc_vocab_free", "ragarc_vocab_size",
-    "ragarc_vocab_encode_split", "ragarc_vocab_encode_split0", "ragarc_rrf_fuse", "ragarc_pool_normalize", "ragarc_mmr_select",
+    "ragarc_vocab_encode_split", "ragarc_vocab_encode_split0", "ragarc_rrf_fuse", "ragarc_rrf_fuse_rows", "ragarc_pool_normalize", "ragarc_mmr_select",
     "ragarc_adjacent_cosine_distance", "ragarc_yes_no_score",
     "ragarc_host_alloc", "ragarc_host_free", "ragarc_index_create", "ragarc_index_free", "ragarc_index_reserve", "ragarc_index_add", "ragarc_index_search",
     "ragarc_index_remove", "ragarc_index_ntotal", "ragarc_index_dim", "ragarc_index_rows",
@@ -140,6 +140,7 @@ def _load():
         "ragarc_bm25_topk": (c_int, [P, P, P, P, P, P, c_double, P, P, c_int, c_int, c_int64, c_int, P, P,
                                      P, c_size_t, P]),
         "ragarc_rrf_fuse": (c_int, [P, c_int, c_int, c_int, c_double, c_int, P, P, P, P]),
+        "ragarc_rrf_fuse_rows": (c_int, [P, P, P, c_int, c_int, c_int, c_double, c_int, P, P, P, P, P, P]),
         "ragarc_pool_normalize": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
         "ragarc_mmr_select": (c_int, [P, c_int64, c_int, c_int, P, c_int, P, c_int, c_int, c_double, P, P]),
     }

@@ -12,6 +12,7 @@ Index build is host work (not the optimisation target); scoring is ``ragarc_bm25
 from __future__ import annotations
 
 import math
+import threading
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -187,27 +188,33 @@ class Bm25Index:
             np.cumsum([len(b) for b in enc], out=offs[1:])
             blob = b"".join(enc)
         cuda = self.device is not None and self.device.type == "cuda"
-        while True:
-            stage = getattr(self, "_enc_stage", None)
-            if stage is None or stage[0].shape[0] < nq or stage[0].shape[1] != tmax:
-                terms = torch.empty((max(nq, 1), tmax), dtype=torch.int32)
-                lens = torch.empty((max(nq, 1),), dtype=torch.int32)
-                if cuda:
-                    terms, lens = terms.pin_memory(), lens.pin_memory()
-                stage = self._enc_stage = (terms, lens)
-            longest = ctypes.c_int(0)
-            if nul_ok:
-                N.check(N.lib.ragarc_vocab_encode_split0(h, blob, len(blob), nq, tmax, stage[0].data_ptr(),
-                                                         stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split0")
-            else:
-                N.check(N.lib.ragarc_vocab_encode_split(h, blob, offs.ctypes.data, nq, tmax, stage[0].data_ptr(),
-                                                        stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split")
-            if longest.value <= tmax:
-                break
-            tmax = 1 << (longest.value - 1).bit_length()                  # a longer query than the staging row: grow, redo
-        width = max(1, longest.value)
-        q_terms = stage[0][:nq, :width].to(self.device, non_blocking=True).contiguous()
-        q_len = stage[1][:nq].to(self.device, non_blocking=True)
+        lock = self.__dict__.setdefault("_enc_lock", threading.Lock())       # retrievers run from thread pools
+        with lock:
+            while True:
+                stage = getattr(self, "_enc_stage", None)
+                if stage is None or stage[0].shape[0] < nq or stage[0].shape[1] != tmax:
+                    terms = torch.empty((max(nq, 1), tmax), dtype=torch.int32)
+                    lens = torch.empty((max(nq, 1),), dtype=torch.int32)
+                    if cuda:
+                        terms, lens = terms.pin_memory(), lens.pin_memory()
+                    stage = self._enc_stage = (terms, lens, torch.cuda.Event() if cuda else None)
+                elif stage[2] is not None:
+                    stage[2].synchronize()          # the previous asynchronous upload out of the buffers is done
+                longest = ctypes.c_int(0)
+                if nul_ok:
+                    N.check(N.lib.ragarc_vocab_encode_split0(h, blob, len(blob), nq, tmax, stage[0].data_ptr(),
+                                                             stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split0")
+                else:
+                    N.check(N.lib.ragarc_vocab_encode_split(h, blob, offs.ctypes.data, nq, tmax, stage[0].data_ptr(),
+                                                            stage[1].data_ptr(), ctypes.byref(longest)), "vocab_encode_split")
+                if longest.value <= tmax:
+                    break
+                tmax = 1 << (longest.value - 1).bit_length()              # a longer query than the staging row: grow, redo
+            width = max(1, longest.value)
+            q_terms = stage[0][:nq, :width].to(self.device, non_blocking=True).contiguous()
+            q_len = stage[1][:nq].to(self.device, non_blocking=True)
+            if stage[2] is not None:
+                stage[2].record(torch.cuda.current_stream(self.device))
         return q_terms, q_len
 
     def encode_queries(self, queries: Iterable[Sequence[str]]):

@@ -56,29 +56,18 @@ class MultiPathRetriever(BaseRetriever):
         if self._canon_cache is not None and self._canon_cache[0] == sig:
             return self._canon_cache[1], self._canon_cache[2]
         keys: Dict[str, int] = {}
-        tables, tabs = [], []
+        tables, doc_arrays = [], []
         for r in self.retrievers:
             docs = r.row_documents()
             tab = np.fromiter((keys.setdefault(d.content, len(keys)) for d in docs), np.int32, len(docs))
-            tabs.append(tab)
-            # device table with one extra trailing -1: indexing it with row -1 (padding) yields key -1
-            tables.append(torch.from_numpy(np.concatenate([tab, np.array([-1], np.int32)])).to(device))
-        # per retriever: key -> the LAST row holding that content (-1: not in this retriever's corpus)
-        key_last_row = np.full((len(self.retrievers), max(len(keys), 1)), -1, np.int64)
-        for l, tab in enumerate(tabs):
-            key_last_row[l, tab] = np.arange(len(tab))       # later rows overwrite earlier ones
-        # the same table on the device (resolution of fused keys to (retriever, row) happens there) and the
-        # documents of every retriever as one object array (row -> Document by fancy indexing, plus a
-        # trailing None that row -1 selects)
-        key_last_row_dev = torch.from_numpy(key_last_row).to(device)
-        doc_arrays = []
-        for r in self.retrievers:
-            docs = r.row_documents()
+            tables.append(torch.from_numpy(tab).to(device))
+            # the documents of the retriever as one object array: row -> Document by fancy indexing, plus a
+            # trailing None that row -1 selects
             arr = np.empty(len(docs) + 1, dtype=object)
             arr[:len(docs)] = docs
             arr[len(docs)] = None
             doc_arrays.append(arr)
-        self._canon_cache = (sig, keys, tables, key_last_row, key_last_row_dev, doc_arrays)
+        self._canon_cache = (sig, keys, tables, doc_arrays)
         return keys, tables
 
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
@@ -89,37 +78,26 @@ class MultiPathRetriever(BaseRetriever):
         device = torch.device(getattr(self.fusion_method, "device", "cuda"))
         _, tables = self._canonical_tables(device)
         nq = len(queries)
-        L = len(self.retrievers)
         per_list = []
         for l, r in enumerate(self.retrievers):
-            keys = None
+            rows = None
             try:
                 if len(r.row_documents()) > 0:
                     rows = r.batch_rows(queries, kl).to(device)
-                    # row -> content key through the device table; -1 rows (padding) stay -1: the table has a
-                    # trailing -1 entry that row -1 indexes
-                    keys = tables[l][rows]
-                    if keys.shape[1] < kl:
-                        keys = torch.nn.functional.pad(keys, (0, kl - keys.shape[1]), value=-1)
             except Exception as exc:  # noqa: BLE001
                 print(f"retriever {type(r).__name__} failed: {exc}")
-                keys = None
-            per_list.append(keys if keys is not None else torch.full((nq, kl), -1, dtype=torch.int32, device=device))
-        ids = torch.stack(per_list, 0)
-        fused_ids, _, counts = self.fusion_method.fuse_batch(ids, top_k)
-        # reference semantics: the Document returned for a content string is the LAST one seen
-        # while walking the lists in retriever order (Fusion.py:61) - i.e. it comes from the last
-        # retriever whose list holds the key; inside one retriever duplicate contents resolve to the
-        # last row carrying them.  Resolved on the device; one small device->host transfer.
-        key_last_row_dev, doc_arrays = self._canon_cache[4], self._canon_cache[5]
-        present = (ids[:, :, None, :] == fused_ids[None, :, :, None]).any(dim=3)       # [L, nq, top_k]
-        last_l = (L - 1) - torch.argmax(present.flip(0).to(torch.uint8), dim=0)        # [nq, top_k]
-        rows = key_last_row_dev[last_l, fused_ids.clamp(min=0).long()]                 # [nq, top_k]
-        rows = torch.where(fused_ids >= 0, rows, torch.full_like(rows, -1))
-        packed = torch.cat([last_l.reshape(-1), rows.reshape(-1), counts.reshape(-1).long()]).cpu().numpy()
-        last_l = packed[:nq * top_k].reshape(nq, top_k)
-        rows = packed[nq * top_k:2 * nq * top_k].reshape(nq, top_k)
-        counts = packed[2 * nq * top_k:]
+                rows = None
+            per_list.append(rows)
+        if all(rows is None for rows in per_list):
+            return [[] for _ in queries]
+        # one launch: row -> content key through the device tables, RRF, and for every fused key the
+        # (retriever, row) of the Document the reference returns for it - the LAST one seen while walking the
+        # lists in retriever order (document_map[content] is overwritten, Fusion.py:61).  One small
+        # device->host transfer brings (list, row, count) back.
+        doc_arrays = self._canon_cache[3]
+        _, _, packed = self.fusion_method.fuse_rows_batch(per_list, tables, kl, top_k)
+        from ... import ops
+        last_l, rows, counts = ops.unpack_fused_rows(packed.cpu().numpy(), nq, top_k)
         # row -> Document by fancy indexing into the per-retriever object arrays (row -1 -> None)
         out = np.empty((nq, top_k), dtype=object)
         for l, arr in enumerate(doc_arrays):

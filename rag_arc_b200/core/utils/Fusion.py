@@ -43,6 +43,12 @@ class RRFusion(FusionMethod):
         from ... import ops
         return ops.rrf_fuse(ids, top_k, float(self.k))
 
+    def fuse_rows_batch(self, rows, row_to_key, kl: int, top_k: int):
+        """The batched hybrid merge on retriever rows (ops.rrf_fuse_rows): fusion plus the (list, row) of the
+        Document the reference's ``document_map`` would hold for every fused key, in one launch."""
+        from ... import ops
+        return ops.rrf_fuse_rows(rows, row_to_key, kl, top_k, float(self.k))
+
     def fuse(self, results: List[List[RetrievalResult]], top_k: int) -> List[RetrievalResult]:
         for ranked in results:                       # Fusion.py:47-49
             for pos, res in enumerate(ranked):

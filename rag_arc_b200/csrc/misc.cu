@@ -241,9 +241,23 @@ __global__ void pool_normalize_kernel(const T* __restrict__ x, const int32_t* __
 // position holding a key owns its score; contributions are added in position order (fp64, each
 // 1.0/(k+rank) correctly rounded) so the sums equal Python's.  Output order = Python's stable
 // sorted(reverse=True): descending score, ties by first appearance.
+//
+// rows != nullptr (ragarc_rrf_fuse_rows): the lists arrive as corpus ROWS of each retriever; the content key
+// of a row comes from that retriever's row -> key table on the way in, and every fused key leaves with the
+// (list, row) of the Document the reference would hand back for it: the one at the LAST position holding
+// the key (document_map[content] is overwritten while walking the lists in order, Fusion.py:61).
+constexpr int RRF_MAX_LISTS = 8;
+struct RrfRows {
+  const int64_t* rows[RRF_MAX_LISTS];       // [nq, kl_each[l]] corpus rows of list l, -1 = padding
+  const int32_t* row_to_key[RRF_MAX_LISTS]; // [corpus rows of list l] content key of a row
+  int kl_each[RRF_MAX_LISTS];
+  int32_t* out_list;                        // [nq, top_k]
+  int64_t* out_row;                         // [nq, top_k]
+};
+
 __global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, int kl, double rrf_k,
                                 int top_k, int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
-                                int32_t* __restrict__ out_count) {
+                                int32_t* __restrict__ out_count, const RrfRows rr, const bool by_rows) {
   extern __shared__ unsigned char rrf_smem[];
   const int n = L * kl;
   double* score = (double*)rrf_smem;                    // [n], valid for owners (< 0: not an owner)
@@ -253,8 +267,19 @@ __global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, 
   const int q = blockIdx.x;
   if (threadIdx.x == 0) n_owner = 0;
   for (int i = threadIdx.x; i < kl; i += blockDim.x) recip[i] = __ddiv_rn(1.0, __dadd_rn(rrf_k, (double)(i + 1)));
-  for (int l = 0; l < L; ++l)
-    for (int i = threadIdx.x; i < kl; i += blockDim.x) key[l * kl + i] = ids[((size_t)l * nq + q) * kl + i];
+  if (by_rows) {
+    for (int l = 0; l < L; ++l) {
+      const int kle = rr.kl_each[l];
+      for (int i = threadIdx.x; i < kl; i += blockDim.x) {
+        int64_t row = -1;
+        if (i < kle && rr.rows[l]) row = rr.rows[l][(size_t)q * kle + i];
+        key[l * kl + i] = row >= 0 ? rr.row_to_key[l][row] : -1;
+      }
+    }
+  } else {
+    for (int l = 0; l < L; ++l)
+      for (int i = threadIdx.x; i < kl; i += blockDim.x) key[l * kl + i] = ids[((size_t)l * nq + q) * kl + i];
+  }
   __syncthreads();
   for (int p = threadIdx.x; p < n; p += blockDim.x) {
     const int32_t me = key[p];
@@ -286,12 +311,21 @@ __global__ void rrf_fuse_kernel(const int32_t* __restrict__ ids, int L, int nq, 
     if (rank < top_k) {
       out_ids[(size_t)q * top_k + rank] = key[p];
       out_scores[(size_t)q * top_k + rank] = s;
+      if (by_rows) {
+        int last = p;
+        for (int j = n - 1; j > p; --j)
+          if (key[j] == key[p]) { last = j; break; }
+        const int l = last / kl;
+        rr.out_list[(size_t)q * top_k + rank] = l;
+        rr.out_row[(size_t)q * top_k + rank] = rr.rows[l][(size_t)q * rr.kl_each[l] + (last - l * kl)];
+      }
     }
   }
   const int cnt = n_owner < top_k ? n_owner : top_k;
   for (int j = cnt + threadIdx.x; j < top_k; j += blockDim.x) {
     out_ids[(size_t)q * top_k + j] = -1;
     out_scores[(size_t)q * top_k + j] = 0.0;
+    if (by_rows) { rr.out_list[(size_t)q * top_k + j] = -1; rr.out_row[(size_t)q * top_k + j] = -1; }
   }
   if (threadIdx.x == 0) out_count[q] = cnt;
 }
@@ -519,7 +553,33 @@ int ragarc_rrf_fuse(const int32_t* ids, int n_lists, int nq, int kl, double rrf_
   int threads = n <= 128 ? 128 : 256;
   if (smem > 48 * 1024) RA_CUDA(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rrf_fuse_kernel<<<nq, threads, smem, (cudaStream_t)stream>>>(ids, n_lists, nq, kl, rrf_k, top_k, out_ids,
-                                                              out_scores, out_count);
+                                                              out_scores, out_count, RrfRows{}, false);
+  RA_LAUNCH_CHECK();
+  return RAGARC_OK;
+}
+
+int ragarc_rrf_fuse_rows(const int64_t* const* rows, const int* kl_each, const int32_t* const* row_to_key,
+                         int n_lists, int nq, int kl, double rrf_k, int top_k, int32_t* out_ids, double* out_scores,
+                         int32_t* out_count, int32_t* out_list, int64_t* out_row, void* stream) {
+  RA_REQUIRE(n_lists > 0 && n_lists <= RRF_MAX_LISTS && nq >= 0 && kl > 0 && top_k > 0,
+             "rrf_fuse_rows: bad shape L=%d (max %d) nq=%d kl=%d top_k=%d", n_lists, RRF_MAX_LISTS, nq, kl, top_k);
+  RA_REQUIRE((int64_t)n_lists * kl <= 4096, "rrf_fuse_rows: L*kl=%d exceeds 4096", n_lists * kl);
+  if (nq == 0) return RAGARC_OK;
+  RA_REQUIRE(rows && kl_each && row_to_key && out_ids && out_scores && out_count && out_list && out_row,
+             "rrf_fuse_rows: null pointer");
+  RrfRows rr{};
+  for (int l = 0; l < n_lists; ++l) {
+    RA_REQUIRE(kl_each[l] >= 0 && kl_each[l] <= kl, "rrf_fuse_rows: list %d has %d columns, kl=%d", l, kl_each[l], kl);
+    RA_REQUIRE(kl_each[l] == 0 || rows[l] == nullptr || row_to_key[l] != nullptr, "rrf_fuse_rows: list %d has rows but no key table", l);
+    rr.rows[l] = rows[l]; rr.row_to_key[l] = row_to_key[l]; rr.kl_each[l] = rows[l] ? kl_each[l] : 0;
+  }
+  rr.out_list = out_list; rr.out_row = out_row;
+  const int n = n_lists * kl;
+  size_t smem = (size_t)n * 8 + (size_t)kl * 8 + (size_t)n * 4;
+  int threads = n <= 128 ? 128 : 256;
+  if (smem > 48 * 1024) RA_CUDA(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rrf_fuse_kernel<<<nq, threads, smem, (cudaStream_t)stream>>>(nullptr, n_lists, nq, kl, rrf_k, top_k, out_ids,
+                                                              out_scores, out_count, rr, true);
   RA_LAUNCH_CHECK();
   return RAGARC_OK;
 }

@@ -417,6 +417,59 @@ def rrf_fuse(ids: torch.Tensor, top_k: int, rrf_k: float = 60.0):
     return out_ids, out_scores, out_count
 
 
+def rrf_fuse_rows(rows, row_to_key, kl: int, top_k: int, rrf_k: float = 60.0):
+    """The hybrid merge on retriever rows in one launch (ragarc_rrf_fuse_rows).  rows: one int64 [nq, <=kl]
+    CUDA tensor per retriever (None = that retriever returned nothing); row_to_key: one int32 CUDA tensor
+    per retriever (row -> content key).  Returns (keys int32 [nq,top_k],
+    scores float64 [nq,top_k], packed) where ``packed`` is ONE uint8 CUDA buffer holding the row of every
+    fused entry in its list's corpus, the list, and the number of entries per query (unpack_fused_rows) -
+    one device->host transfer hands the caller everything it needs to pick the Documents."""
+    L = len(rows)
+    live = [r for r in rows if r is not None]
+    if not live:
+        raise N.RagArcError("rrf_fuse_rows: every list is empty")
+    dev, nq = live[0].device, int(live[0].shape[0])
+    hold = []
+    rp, tp = (ctypes.c_void_p * L)(), (ctypes.c_void_p * L)()
+    ke = (ctypes.c_int * L)()
+    for l, r in enumerate(rows):
+        t = row_to_key[l]
+        _cuda(t, "row_to_key")
+        if t.dtype != torch.int32:
+            raise N.RagArcError("rrf_fuse_rows: row_to_key tables are int32")
+        tp[l] = t.data_ptr()
+        if r is None:
+            rp[l], ke[l] = None, 0
+            continue
+        _cuda(r, "rows")
+        if r.dtype != torch.int64 or r.dim() != 2 or r.shape[0] != nq or r.shape[1] > kl:
+            raise N.RagArcError("rrf_fuse_rows expects int64 [nq, <=kl] rows per list")
+        r = r.contiguous(); hold.append(r)
+        rp[l], ke[l] = r.data_ptr(), int(r.shape[1])
+    out_ids = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+    out_scores = torch.empty((nq, top_k), dtype=torch.float64, device=dev)
+    # one buffer, three views: [rows int64 nq*top_k | lists int32 nq*top_k | counts int32 nq]
+    n = nq * top_k
+    buf = torch.empty((n * 12 + nq * 4,), dtype=torch.uint8, device=dev)
+    out_row = buf[:n * 8].view(torch.int64)
+    out_list = buf[n * 8:n * 12].view(torch.int32)
+    out_count = buf[n * 12:].view(torch.int32)
+    with torch.cuda.device(dev):
+        N.check(N.lib.ragarc_rrf_fuse_rows(rp, ke, tp, L, nq, kl,
+                                           float(rrf_k), top_k, out_ids.data_ptr(), out_scores.data_ptr(),
+                                           out_count.data_ptr(), out_list.data_ptr(), out_row.data_ptr(),
+                                           _stream_ptr(dev)), "rrf_fuse_rows")
+    return out_ids, out_scores, buf
+
+
+def unpack_fused_rows(buf_host, nq: int, top_k: int):
+    """Host views of the buffer rrf_fuse_rows returns (after .cpu().numpy()): (lists [nq,top_k] int32,
+    rows [nq,top_k] int64, counts [nq] int32)."""
+    n = nq * top_k
+    return (buf_host[n * 8:n * 12].view("<i4").reshape(nq, top_k), buf_host[:n * 8].view("<i8").reshape(nq, top_k),
+            buf_host[n * 12:].view("<i4"))
+
+
 _POOL = {"mean": N.POOL_MEAN, "cls": N.POOL_CLS, "last": N.POOL_LAST}
 
 

@@ -87,6 +87,24 @@ def _rrf_fuse(ids, top_k, rrf_k=60.0):
     return torch.from_numpy(out_i), torch.from_numpy(out_s), torch.from_numpy(cnt)
 
 
+def _rrf_fuse_rows(rows, row_to_key, kl, top_k, rrf_k=60.0):
+    """Same packed buffer as ops.rrf_fuse_rows, produced by oracle.rrf.rrf_fuse_rows (integer keys stand in
+    for the content strings)."""
+    live = [r for r in rows if r is not None]
+    nq = int(live[0].shape[0])
+    tabs = [t.numpy() for t in row_to_key]
+    out_i = np.full((nq, top_k), -1, np.int32); out_s = np.zeros((nq, top_k))
+    lists = np.full((nq, top_k), -1, np.int32); rws = np.full((nq, top_k), -1, np.int64); cnt = np.zeros(nq, np.int32)
+    for q in range(nq):
+        per = [([] if r is None else r[q].tolist()) for r in rows]
+        pairs, scores = orrf.rrf_fuse_rows(per, tabs, top_k, rrf_k)
+        for j, ((l, row), sc) in enumerate(zip(pairs, scores)):
+            out_i[q, j] = tabs[l][row]; out_s[q, j] = sc; lists[q, j] = l; rws[q, j] = row
+        cnt[q] = len(pairs)
+    buf = np.concatenate([rws.reshape(-1).view(np.uint8), lists.reshape(-1).view(np.uint8), cnt.view(np.uint8)])
+    return torch.from_numpy(out_i), torch.from_numpy(out_s), torch.from_numpy(buf.copy())
+
+
 def _pool_normalize(x, mask, mode="mean", normalize=True):
     return torch.from_numpy(opool.pool_normalize(x.float().numpy(), mask.numpy(), mode, normalize).astype(np.float32))
 
@@ -132,7 +150,7 @@ def _l2_distances(scores, queries_aug, d):
 def patched():
     from rag_arc_b200 import ops
     fakes = {"normalize_cast": _normalize_cast, "dense_topk": _dense_topk, "mmr_select": _mmr_select,
-             "bm25_scores": _bm25_scores, "bm25_topk": _bm25_topk, "rrf_fuse": _rrf_fuse,
+             "bm25_scores": _bm25_scores, "bm25_topk": _bm25_topk, "rrf_fuse": _rrf_fuse, "rrf_fuse_rows": _rrf_fuse_rows,
              "pool_normalize": _pool_normalize, "l2_aug_dim": _l2_aug_dim, "l2_augment": _l2_augment,
              "l2_distances": _l2_distances}
     saved = {name: getattr(ops, name) for name in fakes}

@@ -376,6 +376,9 @@ def test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fus
     batch = mp.invoke_batch(queries, top_k=10)
     single = [mp.invoke(q, top_k=10) for q in queries]
     assert [[d.content for d in b] for b in batch] == [[d.content for d in s] for s in single]
+    # and the very same Document objects' ids: for duplicated contents the batch hands back the Document at
+    # the LAST position holding the content, as document_map does in the per-query walk (Fusion.py:61)
+    assert [[d.id for d in b] for b in batch] == [[d.id for d in s] for s in single]
 
 
 def test_hybrid_batch_follows_an_update_that_keeps_the_corpus_size(dev):

@@ -136,6 +136,52 @@ def test_rrf_matches_integer_oracle_and_reference_golden(dev):
         assert np.array_equal(got.view(np.uint64), np.array(case["fused_scores"], np.float64).view(np.uint64)), case["name"]
 
 
+def test_rrf_fuse_rows_resolves_documents_like_the_reference_walk(dev):
+    """ragarc_rrf_fuse_rows against oracle.rrf.rrf_fuse_rows (the reference's walk over Documents stated on
+    rows): three retrievers over corpora that share contents (within one corpus and across corpora), lists
+    of different widths, trailing padding, an all-padding list and a retriever that returned nothing; scores
+    bit-exact, (list, row) exact, and the key-level output equal to ragarc_rrf_fuse on the same keys."""
+    rng = np.random.default_rng(11)
+    nq, kl, top_k = 97, 50, 10
+    sizes, widths = [300, 200, 120], [50, 37, 50]
+    n_contents = 260                                                 # < total rows: many duplicates
+    contents = [rng.integers(0, n_contents, n).astype(np.int32) for n in sizes]      # row -> content key
+    rows = [np.stack([rng.permutation(n)[:w] for _ in range(nq)]).astype(np.int64) for n, w in zip(sizes, widths)]
+    rows[0][5, 30:] = -1
+    rows[1][6, :] = -1
+    tabs = [torch.from_numpy(c).to(dev) for c in contents]
+    for variant in ("all", "middle-missing"):
+        dev_rows = [torch.from_numpy(r).to(dev) for r in rows]
+        host_rows = [r for r in rows]
+        if variant == "middle-missing":
+            dev_rows[1] = None
+        out_ids, out_sc, packed = ops.rrf_fuse_rows(dev_rows, tabs, kl, top_k, 60.0)
+        lists, rws, cnt = ops.unpack_fused_rows(packed.cpu().numpy(), nq, top_k)
+        out_ids = out_ids.cpu().numpy(); out_sc = out_sc.cpu().numpy()
+        for q in range(nq):
+            per = [([] if dev_rows[l] is None else host_rows[l][q].tolist()) for l in range(3)]
+            pairs, scores = orrf.rrf_fuse_rows(per, [c.tolist() for c in contents], top_k, 60.0)
+            n = len(pairs)
+            assert cnt[q] == n
+            assert list(zip(lists[q, :n].tolist(), rws[q, :n].tolist())) == pairs, (variant, q)
+            assert np.array_equal(out_sc[q, :n].view(np.uint64), np.array(scores).view(np.uint64))
+            assert out_ids[q, :n].tolist() == [int(contents[l][r]) for l, r in pairs]
+            assert (lists[q, n:] == -1).all() and (rws[q, n:] == -1).all()
+        # same fusion as the key-level entry point on the padded key matrix
+        keys = np.full((3, nq, kl), -1, np.int32)
+        for l in range(3):
+            if dev_rows[l] is not None:
+                r = host_rows[l]
+                keys[l, :, :r.shape[1]] = np.where(r >= 0, contents[l][np.clip(r, 0, None)], -1)
+        k_ids, k_sc, k_n = ops.rrf_fuse(torch.from_numpy(keys).to(dev), top_k)
+        assert np.array_equal(k_ids.cpu().numpy(), out_ids) and np.array_equal(k_n.cpu().numpy(), cnt)
+        assert np.array_equal(k_sc.cpu().numpy().view(np.uint64), out_sc.view(np.uint64))
+    with pytest.raises(Exception):
+        ops.rrf_fuse_rows([None, None, None], tabs, kl, top_k)
+    with pytest.raises(Exception):
+        ops.rrf_fuse_rows([torch.from_numpy(rows[0]).to(dev)] * 9, tabs * 3, kl, top_k)      # more than 8 lists
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("mode", ["mean", "cls", "last"])
 @pytest.mark.parametrize("normalize", [True, False])
