@@ -28,6 +28,30 @@ ts = []
 for _ in range(20):
     t0 = time.perf_counter(); hyb.invoke_batch(queries, top_k=10); ts.append((time.perf_counter() - t0) * 1e3)
 print("invoke_batch ms: median %.3f best %.3f" % (sorted(ts)[10], min(ts)))
+# phases of one call: host work until the fused merge is enqueued / waiting for the device + the one
+# device->host transfer / building the result lists; and the same order reversed (dense first)
+from rag_arc_b200 import ops as _ops
+marks = {}
+_fuse, _unpack = hyb.fusion_method.fuse_rows_batch, _ops.unpack_fused_rows
+def fuse_marked(*a, **kw):
+    r = _fuse(*a, **kw); marks["enqueued"] = time.perf_counter(); return r
+def unpack_marked(*a, **kw):
+    marks["synced"] = time.perf_counter(); return _unpack(*a, **kw)
+hyb.fusion_method.fuse_rows_batch = fuse_marked; _ops.unpack_fused_rows = unpack_marked
+ph = []
+for _ in range(20):
+    t0 = time.perf_counter(); hyb.invoke_batch(queries, top_k=10); t1 = time.perf_counter()
+    ph.append(((marks["enqueued"] - t0) * 1e3, (marks["synced"] - marks["enqueued"]) * 1e3, (t1 - marks["synced"]) * 1e3))
+ph = np.median(np.array(ph), axis=0)
+print("phases ms (median): host work until everything is enqueued %.3f | wait for the device + D2H %.3f | result lists %.3f" % tuple(ph))
+hyb.fusion_method.fuse_rows_batch = _fuse; _ops.unpack_fused_rows = _unpack
+rev = MultiPathRetriever([hyb.retrievers[1], hyb.retrievers[0]], RRFusion(), top_k_per_retriever=k)
+for _ in range(3):
+    rev.invoke_batch(queries, top_k=10)
+ts = []
+for _ in range(20):
+    t0 = time.perf_counter(); rev.invoke_batch(queries, top_k=10); ts.append((time.perf_counter() - t0) * 1e3)
+print("dense first, then BM25: invoke_batch ms: median %.3f best %.3f" % (sorted(ts)[10], min(ts)))
 pr = cProfile.Profile(); pr.enable()
 for _ in range(20):
     hyb.invoke_batch(queries, top_k=10)
