@@ -22,7 +22,7 @@ Printed JSON line (rank 0):
   sustained        a >= 2 s back-to-back run with clocks sampled throughout
   cpu_baseline     N = 1 only: the reference's CPU path timed on this box's host cores
   extra.c4         10M x 1024 fp16 (bge-large shape), batch 1024, k = 100, row-sharded over the N ranks
-  extra.c5         50M x 768 bf16, batch 1 / 8 / 64 (HBM-bound latency regime), row-sharded over N
+  extra.c5         50M x 768 bf16, batch 64 / 32 / 16 / 8 / 4 / 2 / 1 (HBM-bound latency regime), row-sharded over N
   extra.c2         N = 1 only: hybrid BM25 + dense + RRF over 100k documents, batch 256
 """
 from __future__ import annotations
@@ -705,8 +705,9 @@ def measure_dense(ctx, wname, batch, steps, warmup, *, full=False, sustained_s=0
 
 
 def c5_sweep(ctx, steps):
-    """50M x 768 bf16 row-sharded over the ranks, batch 1 / 8 / 64: the corpus is generated once, every
-    batch size gets its own device-timed loop and a synchronous host-in / host-out latency."""
+    """50M x 768 bf16 row-sharded over the ranks, batch 64 ... 1 (Q in {1,2,4,8,16,32,64}): the
+    corpus is generated once, every batch size gets its own device-timed loop and a synchronous host-in /
+    host-out latency."""
     import torch
     from rag_arc_b200 import _native as N
     from rag_arc_b200 import ops
@@ -719,7 +720,7 @@ def c5_sweep(ctx, steps):
     x, n_local = store.index.rows, store.index.ntotal
     sharded = ShardedFlatIndex(x, lo, n_local) if world > 1 else None
     out = {"rows": w["rows"], "dim": w["dim"], "dtype": w["dtype"], "k": w["k"], "rows_per_gpu": n_local, "batches": []}
-    for batch in (64, 8, 1):
+    for batch in (64, 32, 16, 8, 4, 2, 1):
         w["batch"] = batch
         q32, q_dev, q_host = make_queries(ctx, w, batch)
 
