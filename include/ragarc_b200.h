@@ -149,6 +149,8 @@ const void* ragarc_index_rows(const ragarc_index_t* index);
  * concurrently (one stream per shard), gathers the per-shard packed keys (nq*k*8 bytes each) on
  * shard 0's device and merges them with the same key order as a single index - the result is
  * identical for any number of shards.  All buffers are HOST memory; calls are synchronous.
+ * All three metrics are offered; with RAGARC_METRIC_L2 the shards exchange the kept values
+ * q.x - ||x||^2/2 (same order as ascending distance) and the merged values become squared distances.
  * (One process per GPU with a collective in between - rag_arc_b200/sharded.py - is the other form:
  * ragarc_dense_topk_keys per rank, then ragarc_merge_topk_keys[_p2p].)
  */

@@ -345,10 +345,10 @@ static int index_search_keys(ragarc_index* ix, const float* queries_host, int nq
     return order_end(ix, st);
   }
   const size_t q32_bytes = align_up((size_t)nq * ix->d * 4, 256);
-  const size_t qs_bytes = align_up((size_t)nq * ix->d * esize(ix->dtype), 256);
+  const size_t qs_bytes = align_up((size_t)nq * ix->ds * esize(ix->dtype), 256);
   rc = grow_buffer(&ix->stage, &ix->stage_bytes, q32_bytes + qs_bytes, st);
   if (rc) return rc;
-  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->d, ix->dtype, nq, k);
+  const size_t need_ws = ragarc_dense_topk_workspace_bytes(ix->n, ix->ds, ix->dtype, nq, k);
   RA_REQUIRE(need_ws > 0, "sharded_search: unsupported shape (k=%d)", k);
   rc = grow_buffer(&ix->ws, &ix->ws_bytes, need_ws, st);
   if (rc) return rc;
@@ -356,12 +356,17 @@ static int index_search_keys(ragarc_index* ix, const float* queries_host, int nq
   void* qs = (char*)ix->stage + q32_bytes;
   RA_CUDA(cudaMemcpyAsync(q32, queries_host, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, st));
   const void* q_use = q32;
-  if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
+  if (ix->metric == RAGARC_METRIC_L2) {
+    // keys carry q.x - |x|^2/2 (descending = ascending distance); the caller turns the merged values into distances
+    rc = ragarc_l2_augment(q32, qs, nq, ix->d, ix->dtype, 1, 0, nullptr, st);
+    if (rc) return rc;
+    q_use = qs;
+  } else if (ix->dtype != RAGARC_F32 || ix->metric == RAGARC_METRIC_COSINE) {
     rc = ragarc_normalize_cast(q32, qs, nq, ix->d, ix->dtype, ix->metric == RAGARC_METRIC_COSINE, st);
     if (rc) return rc;
     q_use = qs;
   }
-  rc = ragarc_dense_topk_keys(ix->rows, ix->n, ix->d, ix->dtype, q_use, nq, k, id_base, keys, ix->ws, ix->ws_bytes,
+  rc = ragarc_dense_topk_keys(ix->rows, ix->n, ix->ds, ix->dtype, q_use, nq, k, id_base, keys, ix->ws, ix->ws_bytes,
                               RAGARC_DENSE_AUTO, nullptr, st);
   if (rc) return rc;
   return order_end(ix, st);
@@ -376,8 +381,6 @@ int ragarc_sharded_create(int d, int dtype, int metric, int n_shards, const int*
   RA_REQUIRE(out != nullptr, "sharded_create: out is NULL");
   *out = nullptr;
   RA_REQUIRE(n_shards >= 1 && n_shards <= 64, "sharded_create: n_shards=%d", n_shards);
-  RA_REQUIRE(metric == RAGARC_METRIC_IP || metric == RAGARC_METRIC_COSINE,
-             "sharded_create: metric %d is not offered sharded (inner product / cosine only)", metric);
   int ndev = 0;
   RA_CUDA(cudaGetDeviceCount(&ndev));
   ragarc_sharded_index* sh = new (std::nothrow) ragarc_sharded_index();
@@ -497,7 +500,12 @@ int ragarc_sharded_search(ragarc_sharded_index_t* sh, const float* queries_host,
   cudaStream_t s0 = sh->stream[0];
   RA_CUDA(cudaSetDevice(dev0));
   const size_t keys_all = align_up((size_t)G * kb, 256), sc_bytes = align_up((size_t)nq * k * 4, 256);
-  int rc = grow_buffer(&sh->gather, &sh->gather_bytes, keys_all + sc_bytes + (size_t)nq * k * 8, s0);
+  const size_t id_bytes = align_up((size_t)nq * k * 8, 256);
+  const bool l2 = sh->metric == RAGARC_METRIC_L2;
+  const int d_aug = l2 ? ragarc_l2_aug_dim(sh->d, sh->dtype) : 0;
+  const size_t q32_bytes = l2 ? align_up((size_t)nq * sh->d * 4, 256) : 0;
+  const size_t qa_bytes = l2 ? align_up((size_t)nq * d_aug * esize(sh->dtype), 256) : 0;
+  int rc = grow_buffer(&sh->gather, &sh->gather_bytes, keys_all + sc_bytes + id_bytes + q32_bytes + qa_bytes, s0);
   if (rc) return rc;
   char* gb = (char*)sh->gather;
   for (int g = 0; g < G; ++g) {
@@ -508,6 +516,17 @@ int ragarc_sharded_search(ragarc_sharded_index_t* sh, const float* queries_host,
   int64_t* d_ids = (int64_t*)(gb + keys_all + sc_bytes);
   rc = ragarc_merge_topk_keys((const uint64_t*)gb, G, nq, k, k, d_scores, d_ids, s0);
   if (rc) return rc;
+  if (l2) {
+    // merged values q.x - |x|^2/2 -> squared distances |q|^2 - 2(...), with |q|^2 from the queries as every
+    // shard rounded them (the augmented batch is rebuilt here: shard 0 may hold no rows and skip its leg)
+    float* q32 = (float*)(gb + keys_all + sc_bytes + id_bytes);
+    void* qa = gb + keys_all + sc_bytes + id_bytes + q32_bytes;
+    RA_CUDA(cudaMemcpyAsync(q32, queries_host, (size_t)nq * sh->d * 4, cudaMemcpyHostToDevice, s0));
+    rc = ragarc_l2_augment(q32, qa, nq, sh->d, sh->dtype, 1, 0, nullptr, s0);
+    if (rc) return rc;
+    rc = ragarc_l2_distances(d_scores, qa, sh->dtype, nq, k, sh->d, s0);
+    if (rc) return rc;
+  }
   RA_CUDA(cudaMemcpyAsync(out_scores_host, d_scores, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
   RA_CUDA(cudaMemcpyAsync(out_ids_host, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s0));
   RA_CUDA(cudaStreamSynchronize(s0));

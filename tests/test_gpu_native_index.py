@@ -81,7 +81,7 @@ def test_bad_arguments_fail_loudly(dev):
         ix.add(np.zeros((4, 32), np.float32))
 
 
-@pytest.mark.parametrize("dtype,metric", [("float32", "ip"), ("bfloat16", "cosine")])
+@pytest.mark.parametrize("dtype,metric", [("float32", "ip"), ("bfloat16", "cosine"), ("float32", "l2"), ("float16", "l2")])
 def test_single_process_sharded_index_equals_flat_index(dev, dtype, metric):
     """ragarc_sharded_*: three shards (all on device 0 here; tests/test_gpu_multi.py spreads them over
     two GPUs) must return exactly what one flat index returns - same scores bit for bit, same ids."""
