@@ -112,6 +112,64 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* s, int P) {
   __syncthreads();
 }
 
+// The same sort for P = 32*E <= 256 keys by ONE warp, keys in registers (E per lane, key index = lane*E + e):
+// exchanges at a distance below E stay inside a lane, the others are two 32-bit shuffles per key - no
+// shared-memory round trips and no barriers between the 15-36 exchange steps, which is what the
+// shared-memory version spends its time on when only 2-4 of a CTA's warps have work.  Call with warp 0;
+// the other warps wait at the caller's barrier.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_desc(uint64_t* s) {
+  const int lane = threadIdx.x & 31;
+  uint64_t v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = s[lane * E + e];
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= E) {
+        const int lstride = stride / E;
+        // every key of this lane has the same role: low partner iff the lane's bit is clear
+        const bool desc = ((lane * E) & size) == 0, is_lo = (lane & lstride) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const uint32_t ph = __shfl_xor_sync(FULL, (uint32_t)(v[e] >> 32), lstride);
+          const uint32_t pl = __shfl_xor_sync(FULL, (uint32_t)v[e], lstride);
+          const uint64_t o = ((uint64_t)ph << 32) | pl;
+          const bool take_max = is_lo == desc;
+          v[e] = take_max ? (o > v[e] ? o : v[e]) : (o < v[e] ? o : v[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & stride) == 0) {
+            const int idx = lane * E + e;
+            const bool desc = (idx & size) == 0;
+            const uint64_t a = v[e], b = v[e | stride];
+            const bool swap = (a < b) == desc;
+            v[e] = swap ? b : a; v[e | stride] = swap ? a : b;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) s[lane * E + e] = v[e];
+}
+
+// sorts s[0..P) descending; P a power of two >= 32; the block-wide barrier at the end publishes the result
+__device__ __forceinline__ void sort_desc(uint64_t* s, int P) {
+  if (P > 256) { block_bitonic_desc(s, P); return; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (P == 32) warp_bitonic_desc<1>(s);
+    else if (P == 64) warp_bitonic_desc<2>(s);
+    else if (P == 128) warp_bitonic_desc<4>(s);
+    else warp_bitonic_desc<8>(s);
+  }
+  __syncthreads();
+}
+
 // out_keys / out_scores / out_ids point at the [nq,k] blocks; the row of query q is written.
 __device__ __forceinline__ void emit_topk(const uint64_t* s, int q, int k, uint64_t id_base,
                                           uint64_t* out_keys, float* out_scores, int64_t* out_ids) {
@@ -168,6 +226,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
   uint64_t* keys = msm;                       // [smem_keys] (or this query's row of `scratch`, see below)
   uint64_t* win = msm + smem_keys;            // [max(PK, MERGE_WIN)] survivors / winners
   int* offs = (int*)(win + (PK > MERGE_WIN ? PK : MERGE_WIN));   // [S+1]
+  int* lrow = offs + S + 1;                   // [S] row of list s in the [.., cap] list matrix
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sel[3];
   __shared__ uint32_t nwin, omin, omax;
@@ -182,7 +241,11 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     for (int s0 = 0; s0 < S; s0 += 32) {
       const int s = s0 + lane;
       int c = 0;
-      if (s < S) c = counts[(((size_t)(s / sets) * MB + qb) * rows + r) * sets + (s % sets)];
+      if (s < S) {
+        const int row = ((s / sets * MB + qb) * rows + r) * sets + (s % sets);
+        lrow[s] = row;
+        c = counts[row];
+      }
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -216,7 +279,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
         if (e < total_raw) {
           int lo = 0, hi = S;                 // largest sl with offs[sl] <= e
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= e) lo = mid; else hi = mid; }
-          kreg[u] = lists[((((size_t)(lo / sets) * MB + qb) * rows + r) * sets + (lo % sets)) * (size_t)cap + (e - offs[lo])];
+          kreg[u] = lists[(size_t)lrow[lo] * (size_t)cap + (e - offs[lo])];
         }
       }
 #pragma unroll
@@ -303,7 +366,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     const int have = (int)nwin;
     int PW = 32; while (PW < have) PW <<= 1;
     for (int i = have + threadIdx.x; i < PW; i += blockDim.x) win[i] = 0;
-    block_bitonic_desc(win, PW);
+    sort_desc(win, PW);
     emit_topk(win, q, k, id_base, out_keys, out_scores, out_ids);
   } else {
     select_sort_emit(keys, total, k, PK, win, hist, sel, &nwin, orand, q, id_base, out_keys, out_scores, out_ids);
@@ -458,9 +521,9 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const DensePlan
   const int PK = next_pow2(k);
   RA_REQUIRE(tmax <= 16384 && VS <= 1024 && PK <= 2048, "merge: S*sets*keep=%d too large", tmax);
   const int smem_keys = tmax < MERGE_SMEM_KEYS ? tmax : MERGE_SMEM_KEYS;
-  const size_t smem = (size_t)(smem_keys + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(VS + 1) * 4;
+  const size_t smem = (size_t)(smem_keys + (PK > MERGE_WIN ? PK : MERGE_WIN)) * 8 + (size_t)(2 * VS + 1) * 4;
   RA_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (MERGE_SMEM_KEYS + 2048) * 8 + 1025 * 4));
+                               (MERGE_SMEM_KEYS + 2048) * 8 + 2049 * 4));
   MergePush mp{nullptr, 0, 1, 0};
   if (push) mp = *push;
   merge_lists_kernel<<<nq, MERGE_LISTS_THREADS, smem, stream>>>(lists, counts, pl.MB, VS, pl.sets, pl.rows_per_item,
