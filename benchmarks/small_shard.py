@@ -1,6 +1,6 @@
 """The per-rank work of a row-sharded C3 search on ONE GPU: 1024 queries against 1M / G rows for
 G = 1, 2, 4, 8 - whole step (CUDA-graph replay) and the library's own phase events, against the
-tensor roof.  usage: python benchmarks/small_shard.py [steps]"""
+tensor roof.  usage: python benchmarks/small_shard.py [steps] [G,G,...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,7 +12,7 @@ peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.absp
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else {}
 xall = synth.dense_corpus_cuda(1_000_000, 768, torch.bfloat16, dev)
 q, _ = synth.dense_queries_cuda(xall, 1024)
-for G in (8, 4, 2, 1):
+for G in ([int(g) for g in sys.argv[2].split(',')] if len(sys.argv) > 2 else (8, 4, 2, 1)):
     n = 1_000_000 // G
     x = xall[:n]
     step = lambda: ops.dense_topk(x, q, 100, n_rows=n)
