@@ -9,8 +9,9 @@
 // intrinsics (no FMA contraction), is what makes the fp64 sums reproduce numpy's bit for bit.
 //
 // Two schedules:
-//  * bm25_range_kernel (the top-k path): a CTA owns (query, range of 24 576 consecutive docs) and
-//    keeps that range's fp64 accumulators in SHARED memory (192 KB).  Posting lists are sorted by
+//  * bm25_range_kernel (the top-k path): a CTA owns (query, range of consecutive docs) and keeps that
+//    range's fp64 accumulators in SHARED memory: <= 12 288 docs (96 KB) and 512 threads with two CTAs per
+//    SM, or <= 24 576 docs (192 KB) and 1024 threads with one when the corpus is large (bm25_range_geometry).  Posting lists are sorted by
 //    doc, so the range's postings of a term are one contiguous span, found by a warp-cooperative
 //    32-ary search; they are streamed once (coalesced loads of the doc id and the precomputed
 //    per-posting factor, four postings per thread in flight), the read-modify-write stays on chip,
@@ -261,15 +262,15 @@ bm25_range_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                   const int32_t* __restrict__ post_tf, const double* __restrict__ post_val,
                   const double* __restrict__ idf,
                   const double* __restrict__ doc_norm, double k1p1, const int32_t* __restrict__ q_terms,
-                  const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int k,
+                  const int32_t* __restrict__ q_len, int tmax, int64_t n_docs, int k, int range_docs,
                   uint64_t* __restrict__ cand_ord, uint32_t* __restrict__ cand_id) {
-  extern __shared__ double racc[];                 // [RANGE]
+  extern __shared__ double racc[];                 // [range_docs]
   __shared__ TopkScratch S;
   __shared__ int64_t span_lo[32], span_hi[32];
   __shared__ double span_w[32];
   const int range = blockIdx.x, n_ranges = gridDim.x, q = blockIdx.y;
-  const int64_t d0 = (int64_t)range * bm25::RANGE;
-  const int nd = (int)((n_docs - d0) < bm25::RANGE ? (n_docs - d0) : bm25::RANGE);
+  const int64_t d0 = (int64_t)range * range_docs;
+  const int nd = (int)((n_docs - d0) < range_docs ? (n_docs - d0) : range_docs);
   for (int i = threadIdx.x; i < nd; i += blockDim.x) racc[i] = 0.0;
   const int len = q_len[q] < tmax ? q_len[q] : tmax;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -406,10 +407,31 @@ size_t ragarc_bm25_workspace_bytes(int64_t n_docs, int nq) {
   if (cap_rows < 1) cap_rows = 1;
   if (rows > cap_rows) rows = cap_rows;
   size_t dense = rows * row;
-  size_t n_ranges = (size_t)ceil_div(n_docs, bm25::RANGE);
+  size_t n_ranges = (size_t)ceil_div(n_docs, bm25::RANGE / 2);       // the finer of the two geometries
   size_t cand = (size_t)nq * n_ranges * bm25::KMAX * 12 + 512;
   if (cand > (size_t)(1ull << 30)) cand = 0;       // range schedule not used then
   return align_up(dense > cand ? dense : cand, 256);
+}
+
+// Geometry of the range schedule: (docs per CTA, threads per CTA) -> number of ranges.
+//  * half ranges (<= 12 288 docs = 96 KB of accumulators, 512 threads): TWO CTAs per SM, so one CTA's per-term
+//    barriers and its selection overlap the other's posting loop - 0.259 ms against 0.289 ms at C2;
+//  * full ranges (<= 24 576 docs, 1024 threads, one CTA per SM) when the half ranges would make more than
+//    8192 candidates per query for the merge sort.
+// Ranges are balanced (ceil(n / n_ranges) rounded up to 256 docs) so that no CTA is left with a sliver.
+// RAGARC_BM25_RANGE / RAGARC_BM25_THREADS override it for experiments.
+static int64_t bm25_range_geometry(int64_t n_docs, int k, int* range_docs, int* range_threads) {
+  static const int env_range = getenv("RAGARC_BM25_RANGE") ? atoi(getenv("RAGARC_BM25_RANGE")) : 0;
+  static const int env_threads = getenv("RAGARC_BM25_THREADS") ? atoi(getenv("RAGARC_BM25_THREADS")) : 0;
+  int rmax = bm25::RANGE / 2, threads = bm25::THREADS / 2;
+  if (ceil_div(n_docs, rmax) * (int64_t)k > 8192) { rmax = bm25::RANGE; threads = bm25::THREADS; }
+  if (env_range >= 1024 && env_range <= bm25::RANGE) rmax = env_range / 256 * 256;
+  if (env_threads >= 128 && env_threads <= bm25::THREADS) threads = env_threads / 32 * 32;
+  const int64_t nr = ceil_div(n_docs > 0 ? n_docs : 1, rmax);
+  int64_t r = ceil_div(ceil_div(n_docs > 0 ? n_docs : 1, nr), 256) * 256;
+  if (r > rmax) r = rmax;
+  *range_docs = (int)r; *range_threads = threads;
+  return ceil_div(n_docs > 0 ? n_docs : 1, r);
 }
 
 static int bm25_check(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf,
@@ -448,7 +470,8 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
   if (nq == 0) return RAGARC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   // shared-memory range schedule whenever its candidate buffer fits and the merge is one sort
-  const int64_t n_ranges = ceil_div(n_docs, bm25::RANGE);
+  int range_docs, range_threads;
+  const int64_t n_ranges = bm25_range_geometry(n_docs, k, &range_docs, &range_threads);
   int P = 32; while (P < n_ranges * k) P <<= 1;
   const size_t ord_bytes = align_up((size_t)nq * n_ranges * k * 8, 256);
   const size_t cand_bytes = ord_bytes + (size_t)nq * n_ranges * k * 4;
@@ -457,8 +480,9 @@ int ragarc_bm25_topk(const int64_t* indptr, const int32_t* post_doc, const int32
     uint64_t* cand_ord = (uint64_t*)workspace;
     uint32_t* cand_id = (uint32_t*)((char*)workspace + ord_bytes);
     RA_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm25::RANGE_SMEM));
-    bm25_range_kernel<<<dim3((unsigned)n_ranges, (unsigned)nq), bm25::THREADS, bm25::RANGE_SMEM, st>>>(
-        indptr, post_doc, post_tf, post_val, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, k, cand_ord, cand_id);
+    bm25_range_kernel<<<dim3((unsigned)n_ranges, (unsigned)nq), range_threads, (size_t)range_docs * 8, st>>>(
+        indptr, post_doc, post_tf, post_val, idf, doc_norm, k1_plus_1, q_terms, q_len, tmax, n_docs, k, range_docs,
+        cand_ord, cand_id);
     RA_LAUNCH_CHECK();
     const size_t msm = (size_t)P * 12;
     if (msm > 48 * 1024)
