@@ -115,6 +115,33 @@ def gen_rrf(ns):
     return len(cases)
 
 
+def gen_rrf_rows(ns):
+    """The hybrid merge on Documents with DUPLICATED contents (inside one retriever's corpus and across
+    retrievers): which Document object RRFusion.fuse hands back for a content - the last one seen while the
+    lists are walked in order (Fusion.py:61).  Rows and per-retriever row -> content tables go in, (list, row)
+    of every fused Document comes out: the vectors ragarc_rrf_fuse_rows and oracle.rrf.rrf_fuse_rows are
+    checked against."""
+    rng = np.random.default_rng(20250202)
+    cases = []
+    for t in range(16):
+        L = int(rng.integers(1, 4))
+        n_contents = int(rng.integers(8, 60))
+        sizes = [int(rng.integers(10, 80)) for _ in range(L)]
+        contents = [rng.integers(0, n_contents, n).tolist() for n in sizes]           # row -> content key
+        rows = [rng.permutation(n)[:int(rng.integers(0, min(n, 50) + 1))].tolist() for n in sizes]
+        top_k = int(rng.choice([1, 5, 10, 50]))
+        res = [[ns.RetrievalResult(document=ns.Document(content=f"c{contents[l][r]}", id=f"{l}:{r}"), score=1.0)
+                for r in rows[l]] for l in range(L)]
+        fused = ns.RRFusion(k=60.0).fuse(res, top_k)
+        cases.append({"name": f"dups{t}", "rows": rows, "contents": contents, "top_k": top_k, "k": 60.0,
+                      "fused": [[int(x) for x in r.document.id.split(":")] for r in fused],
+                      "fused_scores": [float(r.score) for r in fused]})
+    with open(os.path.join(GOLD, "rrf_rows_reference.json"), "w") as f:
+        json.dump({"source": "core/utils/Fusion.py RRFusion.fuse executed live on Documents with duplicated contents",
+                   "cases": cases}, f, indent=1)
+    return len(cases)
+
+
 def gen_dense(ns):
     rng = np.random.default_rng(42)
     n, d = 300, 48
@@ -274,6 +301,7 @@ def main():
     ns = ref_loader.load()
     os.makedirs(GOLD, exist_ok=True)
     print("rrf cases:", gen_rrf(ns))
+    print("rrf rows cases:", gen_rrf_rows(ns))
     print("dense cases:", gen_dense(ns))
     print("bm25+hybrid cases:", gen_bm25_hybrid(ns))
     print("adjacent cosine pairs:", gen_adjacent_cosine(ns))

@@ -176,6 +176,23 @@ def test_rrf_fuse_rows_resolves_documents_like_the_reference_walk(dev):
         k_ids, k_sc, k_n = ops.rrf_fuse(torch.from_numpy(keys).to(dev), top_k)
         assert np.array_equal(k_ids.cpu().numpy(), out_ids) and np.array_equal(k_n.cpu().numpy(), cnt)
         assert np.array_equal(k_sc.cpu().numpy().view(np.uint64), out_sc.view(np.uint64))
+    # vectors produced by the reference's own RRFusion on Documents with duplicated contents
+    with open(os.path.join(GOLD, "rrf_rows_reference.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        L = len(case["rows"])
+        kl_c = max(1, max(len(r) for r in case["rows"]))
+        d_rows = [torch.tensor([r], dtype=torch.int64, device=dev).reshape(1, len(r)) if len(r) else None for r in case["rows"]]
+        d_tabs = [torch.tensor(t, dtype=torch.int32, device=dev) for t in case["contents"]]
+        if all(r is None for r in d_rows):
+            assert case["fused"] == []
+            continue
+        _, o_sc, packed = ops.rrf_fuse_rows(d_rows, d_tabs, kl_c, case["top_k"], case["k"])
+        lists_, rws_, cnt_ = ops.unpack_fused_rows(packed.cpu().numpy(), 1, case["top_k"])
+        n = int(cnt_[0])
+        assert [[int(a), int(b)] for a, b in zip(lists_[0, :n], rws_[0, :n])] == case["fused"], case["name"]
+        assert np.array_equal(o_sc[0, :n].cpu().numpy().view(np.uint64),
+                              np.array(case["fused_scores"], np.float64).view(np.uint64)), case["name"]
     with pytest.raises(Exception):
         ops.rrf_fuse_rows([None, None, None], tabs, kl, top_k)
     with pytest.raises(Exception):

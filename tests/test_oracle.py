@@ -142,6 +142,27 @@ def test_rrf_golden_and_one_ulp_collision_cases():
         assert 1.0 / (60.0 + a) + 1.0 / (60.0 + b) != 1.0 / (60.0 + c) + 1.0 / (60.0 + d)
 
 
+def test_rrf_rows_oracle_returns_the_document_the_reference_returns_for_duplicated_contents():
+    """tests/golden/rrf_rows_reference.json: the reference's RRFusion.fuse run live on Documents whose contents
+    repeat inside one retriever's corpus and across retrievers - the Document handed back for a content is
+    the last one seen in the walk (Fusion.py:61); oracle.rrf.rrf_fuse_rows must name the same (list, row)."""
+    with open(os.path.join(GOLD, "rrf_rows_reference.json")) as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) >= 16
+    saw_cross_list = False
+    for case in gold["cases"]:
+        texts = [[f"c{x}" for x in tab] for tab in case["contents"]]
+        pairs, scores = orrf.rrf_fuse_rows(case["rows"], texts, case["top_k"], case["k"])
+        assert [list(p) for p in pairs] == case["fused"], case["name"]
+        assert scores == case["fused_scores"], case["name"]
+        first_list = {}
+        for l, rws in enumerate(case["rows"]):
+            for r in rws:
+                first_list.setdefault(case["contents"][l][r], l)
+        saw_cross_list |= any(first_list[case["contents"][l][r]] != l for l, r in pairs)
+    assert saw_cross_list          # some fused Document comes from a later list than the one that introduced its content
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
 def test_rrf_oracle_matches_live_reference_on_random_lists():
     ns = ref_loader.load()
