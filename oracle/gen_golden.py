@@ -224,6 +224,29 @@ def _hybrid_cases(ns, texts, queries, vecs, qvecs, bm):
     return out
 
 
+def _hybrid_tagged_cases(ns, texts, queries, vecs, qvecs):
+    """Same corpus in both retrievers, but DIFFERENT Document objects per text (ids ``b<i>`` in the BM25
+    retriever, ``d<i>`` in the vector store): the ids of the fused results say which retriever's Document the
+    reference hands back - the last one seen in the walk over the lists (Fusion.py:61)."""
+    from oracle.ref_loader import make_bm25_retriever
+    bm = make_bm25_retriever(ns, texts, k=5)
+    for doc in bm.docs:
+        doc.id = "b" + doc.id
+    table = {}
+    for t, v in zip(texts, vecs):
+        table.setdefault(t, v)
+    table.update({q: v for q, v in zip(queries, qvecs)})
+    store = ns.FaissVectorStore.from_texts(texts, TableEmbeddings(table), ids=[f"d{i}" for i in range(len(texts))])
+    dense_r = ns.VectorStoreRetriever(vectorstore=store)
+    out = []
+    for name, retrievers in (("bm25+dense", [bm, dense_r]), ("dense+bm25", [dense_r, bm])):
+        mp = ns.MultiPathRetriever(retrievers, top_k_per_retriever=50)
+        for qi, q in enumerate(queries):
+            for top_k in (10, 50):
+                out.append({"combo": name, "query": qi, "top_k": top_k, "ids": [d_.id for d_ in mp.invoke(q, top_k=top_k)]})
+    return out
+
+
 def gen_bm25_hybrid(ns):
     from oracle.ref_loader import make_bm25_retriever
     rng = np.random.default_rng(7)
@@ -273,6 +296,7 @@ def gen_bm25_hybrid(ns):
         assert len(np.unique(top)) == len(top), "tie inside the top 52 - regenerate with another seed"
         out2["bm25"].append({"query": qi, "scores": [float(x) for x in sc]})
         out2["bm25"].append({"query": qi, "k": 50, "ids": [int(d_.id) for d_ in bm2.invoke(q, k=50)]})
+    out2["hybrid_tagged"] = _hybrid_tagged_cases(ns, texts2, queries2, vecs2, qvecs2)
     np.savez_compressed(os.path.join(GOLD, "hybrid_tiefree.npz"), vecs=vecs2, qvecs=qvecs2)
     with open(os.path.join(GOLD, "hybrid_tiefree.json"), "w") as f:
         json.dump(out2, f)

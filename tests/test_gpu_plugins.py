@@ -353,6 +353,35 @@ def test_hybrid_retriever_equals_reference_multipath_on_tie_free_golden(dev):
     assert [[int(d.id) for d in b] for b in batch] == want
 
 
+def test_hybrid_returns_the_documents_of_the_retriever_the_reference_returns_them_from(dev):
+    """``hybrid_tagged`` in tests/golden/hybrid_tiefree.json: the reference's MultiPathRetriever run live over
+    a BM25 retriever whose Documents carry ids ``b<i>`` and a vector store whose Documents carry ``d<i>`` for the
+    same texts.  Which object comes back for a text found by both is decided by the walk order
+    (Fusion.py:61: the last list holding it); per-query ``invoke`` and the batched ``invoke_batch`` (one
+    ragarc_rrf_fuse_rows launch) must hand back exactly those."""
+    with open(os.path.join(GOLD, "hybrid_tiefree.json")) as f:
+        gold = json.load(f)
+    texts, queries = gold["texts"], gold["queries"]
+    z = np.load(os.path.join(GOLD, "hybrid_tiefree.npz"))
+    table = {}
+    for t, v in zip(texts, z["vecs"]):
+        table.setdefault(t, v)
+    table.update({q: v for q, v in zip(queries, z["qvecs"])})
+    bm = BM25Retriever.from_texts(texts, ids=[f"b{i}" for i in range(len(texts))], k=5, device=dev)
+    store = B200VectorStore.from_texts(texts, TableEmbeddings(table), ids=[f"d{i}" for i in range(len(texts))], device=dev)
+    dense = VectorStoreRetriever(vectorstore=store)
+    combos = {"bm25+dense": [bm, dense], "dense+bm25": [dense, bm]}
+    assert len(gold["hybrid_tagged"]) == 16
+    for name, retrievers in combos.items():
+        mp = MultiPathRetriever(retrievers, fusion_method=RRFusion(device=dev), top_k_per_retriever=50)
+        for top_k in (10, 50):
+            want = [r["ids"] for r in sorted((r for r in gold["hybrid_tagged"] if r["combo"] == name and r["top_k"] == top_k),
+                                             key=lambda r: r["query"])]
+            assert [[d.id for d in mp.invoke(q, top_k=top_k)] for q in queries] == want, (name, top_k)
+            assert [[d.id for d in b] for b in mp.invoke_batch(queries, top_k=top_k)] == want, (name, top_k)
+        assert any(i.startswith("b") for w in want for i in w) and any(i.startswith("d") for w in want for i in w)
+
+
 def test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fusion_oracle(dev):
     """The small golden corpus has duplicate contents and zero-score BM25 tails, where the
     reference's order depends on numpy's unstable argsort; there the check is against the integer

@@ -43,6 +43,10 @@ def test_hybrid_retriever_equals_reference_on_tie_free_golden():
     T.test_hybrid_retriever_equals_reference_multipath_on_tie_free_golden(CPU)
 
 
+def test_hybrid_returns_the_reference_document_objects():
+    T.test_hybrid_returns_the_documents_of_the_retriever_the_reference_returns_them_from(CPU)
+
+
 def test_hybrid_retriever_with_ties_and_duplicates():
     T.test_hybrid_retriever_with_ties_and_duplicate_content_is_consistent_with_fusion_oracle(CPU)
 
