@@ -135,27 +135,31 @@ class FlatIndexB200:
         self.ntotal = 0
 
     def _to_device_f32(self, qt: torch.Tensor) -> torch.Tensor:
-        """Host fp32 queries -> device.  Pageable memory goes through a page-locked staging buffer owned
-        by the index (one CPU copy + an asynchronous DMA instead of the driver's synchronous bounce);
-        the buffer is only rewritten after the previous transfer out of it has completed."""
+        """Host queries -> fp32 on the device.  bf16 / fp16 host tensors cross PCIe as they are (half the bytes
+        of fp32) and are widened on the device, which is exact.  Pageable memory goes through a page-locked
+        staging buffer owned by the index (one CPU copy + an asynchronous DMA instead of the driver's
+        synchronous bounce); the buffer is only rewritten after the previous transfer out of it has completed."""
         if qt.is_cuda or self.device.type != "cuda":
             return qt.to(device=self.device, dtype=torch.float32).contiguous()
-        qt = qt.to(torch.float32).contiguous()
+        if qt.dtype not in (torch.bfloat16, torch.float16):
+            qt = qt.to(torch.float32)
+        qt = qt.contiguous()
+        nbytes = qt.numel() * qt.element_size()
         if qt.is_pinned():
-            return qt.to(self.device, non_blocking=True)
-        if qt.numel() * 4 < (64 << 10):                   # single queries: the driver's inline copy is as fast
-            return qt.to(self.device)
+            return qt.to(self.device, non_blocking=True).to(torch.float32)
+        if nbytes < (64 << 10):                           # single queries: the driver's inline copy is as fast
+            return qt.to(self.device).to(torch.float32)
         with self._stage_lock:                             # retrievers run from thread pools (base.py:82-96)
             st = getattr(self, "_q_stage", None)
-            if st is None or st[0].numel() < qt.numel():
-                st = self._q_stage = (torch.empty((qt.numel(),), dtype=torch.float32).pin_memory(), torch.cuda.Event())
+            if st is None or st[0].numel() < nbytes:
+                st = self._q_stage = (torch.empty((nbytes,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
             else:
                 st[1].synchronize()                        # the previous transfer out of the buffer is done
-            view = st[0][:qt.numel()].view(qt.shape)
+            view = st[0][:nbytes].view(qt.dtype).view(qt.shape)
             view.copy_(qt)
             dev = view.to(self.device, non_blocking=True)
             st[1].record(torch.cuda.current_stream(self.device))
-        return dev
+        return dev.to(torch.float32)
 
     def prepare_queries(self, q) -> torch.Tensor:
         qt = torch.as_tensor(q)

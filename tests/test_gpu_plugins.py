@@ -183,6 +183,24 @@ def test_search_pipeline_equals_synchronous_search(dev):
     assert torch.equal(r2, r) and torch.equal(s2, s)
 
 
+@pytest.mark.parametrize("hdt", [torch.bfloat16, torch.float16])
+def test_half_precision_host_queries_equal_their_fp32_widening(dev, hdt):
+    """bf16 / fp16 HOST query tensors cross PCIe as halves and are widened on the device: the results must equal
+    those of the same values handed over as fp32 - pageable (page-locked staging above 64 KB, inline copy
+    below) and pinned."""
+    rng = np.random.default_rng(12)
+    vecs = rng.standard_normal((6000, 256)).astype(np.float32)
+    store = B200VectorStore.from_embeddings([f"t{i}" for i in range(6000)], vecs, dtype="bfloat16", metric="cosine", device=dev)
+    for nq in (200, 3):                                   # 100 KB -> staging buffer; 1.5 KB -> inline copy
+        q = torch.from_numpy(rng.standard_normal((nq, 256)).astype(np.float32)).to(hdt)
+        ws, wr = store.search_batch(q.float(), 9)
+        for variant in (q, q.pin_memory(), q.numpy() if hdt == torch.float16 else q):
+            s, r = store.search_batch(variant, 9)
+            assert torch.equal(r, wr) and torch.equal(s, ws)
+        s, r = store.search_batch(q, 9)                   # staging buffer reused
+        assert torch.equal(r, wr) and torch.equal(s, ws)
+
+
 @pytest.mark.parametrize("metric,dtype", [("cosine", "bfloat16"), ("l2", "float16")])
 def test_overlapped_capture_equals_plain_search(dev, metric, dtype):
     """capture_search_overlapped: scoring of call i+1 on one stream, selection of call i on another, two
