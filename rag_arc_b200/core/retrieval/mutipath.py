@@ -53,8 +53,9 @@ class MultiPathRetriever(BaseRetriever):
         the same number of documents moves rows without changing the size)."""
         sig = tuple((id(r), r.corpus_stamp()) if hasattr(r, "corpus_stamp")
                     else (id(r), id(r.row_documents()), len(r.row_documents())) for r in self.retrievers)
-        if self._canon_cache is not None and self._canon_cache[0] == sig:
-            return self._canon_cache[1], self._canon_cache[2]
+        cache = self._canon_cache                  # one read: another thread may replace it meanwhile
+        if cache is not None and cache[0] == sig:
+            return cache[1], cache[2], cache[3]
         keys: Dict[str, int] = {}
         tables, doc_arrays = [], []
         for r in self.retrievers:
@@ -68,7 +69,7 @@ class MultiPathRetriever(BaseRetriever):
             arr[len(docs)] = None
             doc_arrays.append(arr)
         self._canon_cache = (sig, keys, tables, doc_arrays)
-        return keys, tables
+        return keys, tables, doc_arrays
 
     def invoke_batch(self, queries: List[str], **kwargs: Any) -> List[List[Document]]:
         top_k = kwargs.get("top_k", 10)
@@ -76,7 +77,7 @@ class MultiPathRetriever(BaseRetriever):
             return [self.invoke(q, **kwargs) for q in queries]
         kl = self.top_k_per_retriever
         device = torch.device(getattr(self.fusion_method, "device", "cuda"))
-        _, tables = self._canonical_tables(device)
+        _, tables, doc_arrays = self._canonical_tables(device)
         nq = len(queries)
         per_list = []
         for l, r in enumerate(self.retrievers):
@@ -94,7 +95,6 @@ class MultiPathRetriever(BaseRetriever):
         # (retriever, row) of the Document the reference returns for it - the LAST one seen while walking the
         # lists in retriever order (document_map[content] is overwritten, Fusion.py:61).  One small
         # device->host transfer brings (list, row, count) back.
-        doc_arrays = self._canon_cache[3]
         _, _, packed = self.fusion_method.fuse_rows_batch(per_list, tables, kl, top_k)
         from ... import ops
         last_l, rows, counts = ops.unpack_fused_rows(packed.cpu().numpy(), nq, top_k)
